@@ -1,0 +1,58 @@
+// common.cuh -- shared helpers for the pb200 line-by-line engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace pb200 {
+
+// Physical / numerical constants with the values of the reference's C layer
+// (src_c/include/constants.h:5-21).  These deliberately differ from the CODATA values
+// the reference's Python layer uses for densities.
+constexpr double kPi = 3.141592653589793;
+constexpr double kSqrtLn2 = 0.83255461115769775635;
+constexpr double kTwoOverSqrtPi = 1.12837916709551257389;
+constexpr double kSqrtLn2OverPi = 0.46971863934982566689;
+constexpr double kLightSpeed = 2.99792458e10;
+constexpr double kBoltzmann = 1.380658e-16;
+constexpr double kAmu = 1.66053886e-24;
+constexpr double kPlanck = 6.6260755e-27;
+constexpr double kECharge = 4.8032068e-10;
+constexpr double kEMass = 9.1093897e-28;
+// SIGCTE, EXPCTE (constants.h:20-21), folded left to right in IEEE double.
+constexpr double kSigCte = kPi * kECharge * kECharge / kLightSpeed / kLightSpeed / kEMass;
+constexpr double kExpCte = kPlanck * kLightSpeed / kBoltzmann;
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t err, const char *what, const char *file, int line);
+
+#define PB_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t _e = (call);                                             \
+        if (_e != cudaSuccess) return pb200::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// IEEE round-to-nearest primitives that the compiler may not contract into FMAs.
+// Every value that feeds a discrete decision of the reference (an index, a comparison)
+// is computed with these so that it rounds exactly like the reference's C expression.
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dadd_rn(a, -b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// Nearest grid index with the semantics of pyramidsearch (src_c/include/utils.h:44-72)
+// for a monotonically increasing query sequence: clamp outside the grid, otherwise the
+// closer of the two bracketing samples, ties to the lower index.
+__device__ __forceinline__ int nearest_index(const double *grid, int n, double v) {
+    if (v < grid[0]) return 0;
+    if (grid[n - 1] < v) return n - 1;
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        int mid = (hi + lo) >> 1;
+        if (grid[mid] < v) lo = mid; else hi = mid;
+    }
+    return (fabs(dsub(grid[hi], v)) < fabs(dsub(grid[lo], v))) ? hi : lo;
+}
+
+}  // namespace pb200

@@ -1,0 +1,902 @@
+// engine.cu -- host side of the pb200 engine and its C ABI (include/pb200_lbl.h).
+//
+// The handle owns device copies of every (T,p)-independent input of the reference's
+// ec.extinction call (spectral grids, Voigt table, line list) plus the static line
+// pre-processing; a batch call evaluates any number of (T,p) units with two kernels per
+// chunk (strengths, accumulate).  See DESIGN.md for the data layout.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pb200_lbl.h"
+#include "lbl_kernels.cuh"
+#include "voigt.cuh"
+
+namespace pb200 {
+
+static thread_local std::string g_error;
+
+void set_error(const std::string &msg) { g_error = msg; }
+
+int cuda_fail(cudaError_t err, const char *what, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d in %s", (int)err,
+             cudaGetErrorString(err), file, line, what);
+    g_error = buf;
+    if (err == cudaErrorNoDevice || err == cudaErrorInsufficientDriver) return PB200_ENODEVICE;
+    if (err == cudaErrorMemoryAllocation) return PB200_ENOMEM;
+    return PB200_ECUDA;
+}
+
+static int fail(int code, const std::string &msg) {
+    g_error = msg;
+    return code;
+}
+
+static int select_device(int device) {
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(PB200_ENODEVICE,
+                    "no usable CUDA device: this engine has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(PB200_EINVAL, "device index out of range");
+    PB_CUDA(cudaSetDevice(device));
+    return 0;
+}
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(size_t count) {
+        if (count <= n && p) return 0;
+        release();
+        if (count == 0) return 0;
+        PB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        n = count;
+        return 0;
+    }
+    int upload(const T *src, size_t count, cudaStream_t st) {
+        int rc = alloc(count);
+        if (rc) return rc;
+        if (count) PB_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+};
+
+// binsearchapprox (src_c/include/utils.h:75-89): bisection keeping a[lo] <= v < a[hi],
+// then the closer end, ties to the lower index.
+static int nearest_bisect(const double *a, double v, int lo, int hi) {
+    while (hi - lo > 1) {
+        const int mid = (hi + lo) / 2;
+        if (a[mid] > v) hi = mid; else lo = mid;
+    }
+    return (std::fabs(a[hi] - v) < std::fabs(a[lo] - v)) ? hi : lo;
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+struct pb200_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    int64_t launches = 0;
+    double timing[5] = {0, 0, 0, 0, 0};
+
+    // grids
+    bool has_grid = false;
+    int64_t nwave = 0, onwn = 0;
+    std::vector<double> wn, own;
+    std::vector<int64_t> divisors;
+    DevBuf<double> d_wn;
+
+    // voigt
+    bool has_voigt = false;
+    int nlor = 0, ndop = 0;
+    double cutoff = 0.0;
+    std::vector<double> lorentz, doppler;
+    std::vector<int> psize;
+    std::vector<long long> pindex;
+    int64_t profile_len = 0;
+    DevBuf<double> d_profile, d_doppler;
+    DevBuf<int> d_psize;
+    DevBuf<long long> d_pindex;
+
+    // species
+    bool has_species = false;
+    int nmol = 0, niso = 0;
+    std::vector<double> mol_radius, mol_mass, iso_mass, iso_ratio;
+    std::vector<int> iso_imol;
+    DevBuf<double> d_iso_ratio;
+
+    // partition tables
+    int pf_ntemp = 0;
+    std::vector<double> pf_temp, pf_z;
+
+    // lines
+    bool has_lines = false;
+    int64_t n_inwin = 0, ngroups = 0, nadd = 0;
+    std::vector<int64_t> iso_nadd;  // absorbed lines per isotope
+    DevBuf<double> d_lwn, d_lelow, d_lgf, d_gwn;
+    DevBuf<int> d_giown, d_gbin;
+    DevBuf<unsigned int> d_gstart;
+    DevBuf<unsigned short> d_giso;
+    int nbins = 0, binw = 1;
+
+    // per-batch scratch (grown on demand)
+    DevBuf<double> d_ksum, d_tp_temp, d_tp_isoz, d_out;
+    DevBuf<unsigned long long> d_kmax, d_counters;
+    DevBuf<UnitParams> d_units;
+    DevBuf<IsoUnit> d_iso_units;
+    DevBuf<int> d_iso_row;
+
+    StaticView view() const {
+        StaticView V;
+        V.wn = d_wn.p;
+        V.nwave = (int)nwave;
+        V.onwn = onwn;
+        V.own0 = own.empty() ? 0.0 : own[0];
+        V.ownstep = own.size() > 1 ? own[1] - own[0] : 0.0;
+        V.own_last = own.empty() ? 0.0 : own[onwn - 1];
+        V.wn0 = wn.empty() ? 0.0 : wn[0];
+        V.profile = d_profile.p;
+        V.psize = d_psize.p;
+        V.pindex = d_pindex.p;
+        V.doppler = d_doppler.p;
+        V.nlor = nlor;
+        V.ndop = ndop;
+        V.l_wn = d_lwn.p;
+        V.l_elow = d_lelow.p;
+        V.l_gf = d_lgf.p;
+        V.g_wn = d_gwn.p;
+        V.g_iown = d_giown.p;
+        V.g_start = d_gstart.p;
+        V.g_iso = d_giso.p;
+        V.ngroups = ngroups;
+        V.gbin = d_gbin.p;
+        V.nbins = nbins;
+        V.binw = binw;
+        V.niso = niso;
+        V.iso_ratio = d_iso_ratio.p;
+        return V;
+    }
+};
+
+extern "C" {
+
+const char *pb200_last_error(void) { return g_error.c_str(); }
+const char *pb200_version(void) { return "pb200-lbl 0.1 (sm_100a)"; }
+
+int pb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ----------------------------------------------------------------------------------------
+int pb200_voigt_grid(int device, int nlor, int ndop, const double *lorentz,
+                     const double *doppler, double dwn, int64_t *psize, int64_t *pindex,
+                     double *profile, int64_t profile_len) {
+    if (nlor <= 0 || ndop <= 0 || !lorentz || !doppler || !psize || !pindex || !profile)
+        return fail(PB200_EINVAL, "pb200_voigt_grid: null or empty argument");
+    int rc = select_device(device);
+    if (rc) return rc;
+    VoigtPlan plan;
+    if (voigt_plan(nlor, ndop, psize, pindex, &plan)) return PB200_EINVAL;
+    if (plan.total > profile_len)
+        return fail(PB200_EINVAL, "pb200_voigt_grid: profile array shorter than sum(2*size+1)");
+    DevBuf<double> d_prof;
+    rc = d_prof.alloc((size_t)plan.total);
+    if (rc) return rc;
+    cudaStream_t st;
+    PB_CUDA(cudaStreamCreate(&st));
+    rc = voigt_launch(st, plan, lorentz, doppler, dwn, d_prof.p, nullptr);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(profile, d_prof.p, sizeof(double) * plan.total,
+                                        cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "copy profile", __FILE__, __LINE__);
+    }
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+// ----------------------------------------------------------------------------------------
+int pb200_engine_create(int device, pb200_engine **out) {
+    if (!out) return fail(PB200_EINVAL, "pb200_engine_create: null output");
+    *out = nullptr;
+    int rc = select_device(device);
+    if (rc) return rc;
+    pb200_engine *e = new pb200_engine();
+    e->device = device;
+    cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && err == cudaSuccess; i++) err = cudaEventCreate(&e->ev[i]);
+    if (err != cudaSuccess) {
+        delete e;
+        return cuda_fail(err, "engine create", __FILE__, __LINE__);
+    }
+    *out = e;
+    return 0;
+}
+
+void pb200_engine_destroy(pb200_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) {
+        cudaStreamSynchronize(e->stream);
+        cudaStreamDestroy(e->stream);
+    }
+    for (int i = 0; i < 6; i++)
+        if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    delete e;
+}
+
+int pb200_engine_set_grid(pb200_engine *e, const double *wn, int64_t nwave, const double *own,
+                          int64_t onwn, const int64_t *divisors, int ndivs) {
+    if (!e || !wn || !own || !divisors || nwave < 2 || onwn < 2 || ndivs < 1)
+        return fail(PB200_EINVAL, "pb200_engine_set_grid: need nwave>=2, onwn>=2, ndivs>=1");
+    if (onwn > 0x7ffffff0LL || nwave > 0x7ffffff0LL)
+        return fail(PB200_EINVAL, "pb200_engine_set_grid: grids limited to 2^31 samples "
+                                  "(the reference indexes them with C int)");
+    PB_CUDA(cudaSetDevice(e->device));
+    e->wn.assign(wn, wn + nwave);
+    e->own.assign(own, own + onwn);
+    e->divisors.assign(divisors, divisors + ndivs);
+    e->nwave = nwave;
+    e->onwn = onwn;
+    int rc = e->d_wn.upload(wn, (size_t)nwave, e->stream);
+    if (rc) return rc;
+    PB_CUDA(cudaStreamSynchronize(e->stream));
+    e->has_grid = true;
+    e->has_lines = false;  // grouping depends on the fine grid
+    return 0;
+}
+
+static int adopt_voigt_tables(pb200_engine *e, int nlor, int ndop, const double *lorentz,
+                              const double *doppler, const int64_t *psize,
+                              const int64_t *pindex, double cutoff) {
+    e->nlor = nlor;
+    e->ndop = ndop;
+    e->cutoff = cutoff;
+    e->lorentz.assign(lorentz, lorentz + nlor);
+    e->doppler.assign(doppler, doppler + ndop);
+    e->psize.resize((size_t)nlor * ndop);
+    e->pindex.resize((size_t)nlor * ndop);
+    for (size_t i = 0; i < (size_t)nlor * ndop; i++) {
+        if (psize[i] < 0 || psize[i] > 0x3fffffff)
+            return fail(PB200_EINVAL, "voigt: half-size out of range");
+        e->psize[i] = (int)psize[i];
+        e->pindex[i] = (long long)pindex[i];
+    }
+    int rc = e->d_psize.upload(e->psize.data(), e->psize.size(), e->stream);
+    if (!rc) rc = e->d_pindex.upload(e->pindex.data(), e->pindex.size(), e->stream);
+    if (!rc) rc = e->d_doppler.upload(doppler, (size_t)ndop, e->stream);
+    if (rc) return rc;
+    PB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int pb200_engine_build_voigt(pb200_engine *e, int nlor, int ndop, const double *lorentz,
+                             const double *doppler, double dwn, int64_t *psize,
+                             int64_t *pindex, double cutoff) {
+    if (!e || nlor <= 0 || ndop <= 0 || !lorentz || !doppler || !psize || !pindex)
+        return fail(PB200_EINVAL, "pb200_engine_build_voigt: null or empty argument");
+    PB_CUDA(cudaSetDevice(e->device));
+    // The table length follows the reference: sum(2*size+1) over the *input* sizes, where
+    // skipped entries count one sample (pyrat/voigt.py:142), leaving zero padding at the end.
+    int64_t alloc_len = 0;
+    for (size_t i = 0; i < (size_t)nlor * ndop; i++) alloc_len += 2 * psize[i] + 1;
+    VoigtPlan plan;
+    if (voigt_plan(nlor, ndop, psize, pindex, &plan)) return PB200_EINVAL;
+    if (alloc_len < plan.total) alloc_len = plan.total;
+    e->d_profile.release();
+    int rc = e->d_profile.alloc((size_t)alloc_len);
+    if (rc) return rc;
+    PB_CUDA(cudaMemsetAsync(e->d_profile.p, 0, sizeof(double) * alloc_len, e->stream));
+    rc = voigt_launch(e->stream, plan, lorentz, doppler, dwn, e->d_profile.p, &e->launches);
+    if (rc) return rc;
+    e->profile_len = alloc_len;
+    rc = adopt_voigt_tables(e, nlor, ndop, lorentz, doppler, psize, pindex, cutoff);
+    if (rc) return rc;
+    e->has_voigt = true;
+    return 0;
+}
+
+int pb200_engine_set_voigt(pb200_engine *e, int nlor, int ndop, const double *lorentz,
+                           const double *doppler, const int64_t *psize, const int64_t *pindex,
+                           const double *profile, int64_t profile_len, double cutoff) {
+    if (!e || nlor <= 0 || ndop <= 0 || !lorentz || !doppler || !psize || !pindex || !profile ||
+        profile_len <= 0)
+        return fail(PB200_EINVAL, "pb200_engine_set_voigt: null or empty argument");
+    PB_CUDA(cudaSetDevice(e->device));
+    for (size_t i = 0; i < (size_t)nlor * ndop; i++)
+        if (pindex[i] < 0 || pindex[i] + 2 * psize[i] + 1 > profile_len)
+            return fail(PB200_EINVAL, "pb200_engine_set_voigt: profile index out of bounds");
+    e->d_profile.release();
+    int rc = e->d_profile.upload(profile, (size_t)profile_len, e->stream);
+    if (rc) return rc;
+    e->profile_len = profile_len;
+    rc = adopt_voigt_tables(e, nlor, ndop, lorentz, doppler, psize, pindex, cutoff);
+    if (rc) return rc;
+    e->has_voigt = true;
+    return 0;
+}
+
+int64_t pb200_engine_profile_len(const pb200_engine *e) { return e ? e->profile_len : 0; }
+
+int pb200_engine_get_profile(pb200_engine *e, double *profile, int64_t profile_len) {
+    if (!e || !profile) return fail(PB200_EINVAL, "pb200_engine_get_profile: null argument");
+    if (!e->has_voigt) return fail(PB200_ESTATE, "pb200_engine_get_profile: no Voigt table");
+    if (profile_len < e->profile_len)
+        return fail(PB200_EINVAL, "pb200_engine_get_profile: destination too short");
+    PB_CUDA(cudaSetDevice(e->device));
+    PB_CUDA(cudaMemcpyAsync(profile, e->d_profile.p, sizeof(double) * e->profile_len,
+                            cudaMemcpyDeviceToHost, e->stream));
+    PB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int pb200_engine_set_species(pb200_engine *e, int nmol, const double *mol_radius,
+                             const double *mol_mass, int niso, const int64_t *iso_imol,
+                             const double *iso_mass, const double *iso_ratio) {
+    if (!e || nmol <= 0 || niso <= 0 || !mol_radius || !mol_mass || !iso_imol || !iso_mass ||
+        !iso_ratio)
+        return fail(PB200_EINVAL, "pb200_engine_set_species: null or empty argument");
+    if (niso > kMaxIso) return fail(PB200_EINVAL, "pb200_engine_set_species: too many isotopes");
+    for (int i = 0; i < niso; i++)
+        if (iso_imol[i] < 0 || iso_imol[i] >= nmol)
+            return fail(PB200_EINVAL, "pb200_engine_set_species: iso_imol out of range");
+    PB_CUDA(cudaSetDevice(e->device));
+    e->nmol = nmol;
+    e->niso = niso;
+    e->mol_radius.assign(mol_radius, mol_radius + nmol);
+    e->mol_mass.assign(mol_mass, mol_mass + nmol);
+    e->iso_mass.assign(iso_mass, iso_mass + niso);
+    e->iso_ratio.assign(iso_ratio, iso_ratio + niso);
+    e->iso_imol.resize(niso);
+    for (int i = 0; i < niso; i++) e->iso_imol[i] = (int)iso_imol[i];
+    int rc = e->d_iso_ratio.upload(iso_ratio, (size_t)niso, e->stream);
+    if (rc) return rc;
+    PB_CUDA(cudaStreamSynchronize(e->stream));
+    e->has_species = true;
+    e->has_lines = false;
+    return 0;
+}
+
+int pb200_engine_set_partition(pb200_engine *e, int ntemp, const double *temp, const double *z) {
+    if (!e || ntemp < 2 || !temp || !z)
+        return fail(PB200_EINVAL, "pb200_engine_set_partition: need ntemp>=2");
+    if (!e->has_species) return fail(PB200_ESTATE, "pb200_engine_set_partition: set_species first");
+    for (int i = 1; i < ntemp; i++)
+        if (!(temp[i] > temp[i - 1]))
+            return fail(PB200_EINVAL, "pb200_engine_set_partition: temperatures must increase");
+    e->pf_ntemp = ntemp;
+    e->pf_temp.assign(temp, temp + ntemp);
+    e->pf_z.assign(z, z + (size_t)ntemp * e->niso);
+    return 0;
+}
+
+// Static line pre-processing: everything in _extcoeff.c:229-262 that does not depend on (T,p).
+int pb200_engine_set_lines(pb200_engine *e, int64_t nlines, const double *wn,
+                           const double *elow, const double *gf, const int64_t *iso_id) {
+    if (!e || nlines < 0 || (nlines > 0 && (!wn || !elow || !gf || !iso_id)))
+        return fail(PB200_EINVAL, "pb200_engine_set_lines: null argument");
+    if (!e->has_grid || !e->has_species)
+        return fail(PB200_ESTATE, "pb200_engine_set_lines: set_grid and set_species first");
+    if (nlines > 0x7ffffff0LL)
+        return fail(PB200_EINVAL, "pb200_engine_set_lines: more than 2^31 lines "
+                                  "(TLI n_transitions is int32, lread.py:299)");
+    PB_CUDA(cudaSetDevice(e->device));
+    const int niso = e->niso;
+    const double *own = e->own.data();
+    const int64_t onwn = e->onwn;
+    const double own0 = own[0], own_last = own[onwn - 1];
+    const double ownstep = own[1] - own[0];
+
+    // Isotopes must come in contiguous blocks, ascending wavenumber inside (TLI layout).
+    std::vector<char> seen(niso, 0);
+    for (int64_t ln = 0; ln < nlines; ln++) {
+        const int64_t i = iso_id[ln];
+        if (i < 0 || i >= niso)
+            return fail(PB200_EINVAL, "pb200_engine_set_lines: isotope id out of range");
+        if (ln == 0 || iso_id[ln - 1] != i) {
+            if (seen[i])
+                return fail(PB200_EINVAL, "pb200_engine_set_lines: an isotope appears in more "
+                                          "than one block; lines must be grouped by isotope");
+            seen[i] = 1;
+        } else if (wn[ln] < wn[ln - 1]) {
+            return fail(PB200_EINVAL, "pb200_engine_set_lines: wavenumbers must ascend within "
+                                      "each isotope block");
+        }
+    }
+
+    std::vector<double> l_wn, l_elow, l_gf, g_wn;
+    std::vector<int> g_iown;
+    std::vector<unsigned int> g_start;
+    std::vector<unsigned short> g_iso;
+    l_wn.reserve(nlines);
+    l_elow.reserve(nlines);
+    l_gf.reserve(nlines);
+    e->iso_nadd.assign(niso, 0);
+    int64_t nadd = 0;
+    for (int64_t ln = 0; ln < nlines; ln++) {
+        const double w = wn[ln];
+        if (w < own0 || w > own_last) continue;  // :215,239
+        const int iso = (int)iso_id[ln];
+        int iown = (int)((w - own0) / ownstep);  // :243
+        if (iown + 1 < onwn && std::fabs(w - own[iown + 1]) < std::fabs(w - own[iown])) iown++;
+        g_wn.push_back(w);
+        g_iown.push_back(iown);
+        g_iso.push_back((unsigned short)iso);
+        g_start.push_back((unsigned int)l_wn.size());
+        l_wn.push_back(w);
+        l_elow.push_back(elow[ln]);
+        l_gf.push_back(gf[ln]);
+        // :249-262 absorb the following lines that fall on the same fine sample
+        while (ln + 1 != nlines && iso_id[ln + 1] == iso && wn[ln + 1] <= own_last) {
+            if (std::fabs(wn[ln + 1] - own[iown]) < ownstep) {
+                ln++;
+                nadd++;
+                e->iso_nadd[iso]++;
+                l_wn.push_back(wn[ln]);
+                l_elow.push_back(elow[ln]);
+                l_gf.push_back(gf[ln]);
+            } else {
+                break;
+            }
+        }
+    }
+    g_start.push_back((unsigned int)l_wn.size());
+    const int64_t ngroups = (int64_t)g_wn.size();
+
+    // Coarse per-isotope index over the fine grid.
+    int binw = (int)std::max<int64_t>(64, onwn >> 16);
+    int nbins = (int)((onwn + binw - 1) / binw);
+    std::vector<int> gbin((size_t)niso * (nbins + 1), 0);
+    {
+        int64_t g = 0;
+        // groups are in line order: isotope blocks, ascending iown inside each block
+        std::vector<int64_t> beg(niso, -1), end(niso, -1);
+        for (g = 0; g < ngroups; g++) {
+            const int iso = g_iso[g];
+            if (beg[iso] < 0) beg[iso] = g;
+            end[iso] = g + 1;
+        }
+        for (int iso = 0; iso < niso; iso++) {
+            int *gb = gbin.data() + (size_t)iso * (nbins + 1);
+            if (beg[iso] < 0) {
+                for (int b = 0; b <= nbins; b++) gb[b] = 0;
+                continue;
+            }
+            int64_t cur = beg[iso];
+            for (int b = 0; b <= nbins; b++) {
+                const int64_t edge = (int64_t)b * binw;
+                while (cur < end[iso] && g_iown[cur] < edge) cur++;
+                gb[b] = (int)cur;
+            }
+            gb[nbins] = (int)end[iso];
+        }
+    }
+
+    cudaStream_t st = e->stream;
+    int rc = 0;
+    if (!rc) rc = e->d_lwn.upload(l_wn.data(), l_wn.size(), st);
+    if (!rc) rc = e->d_lelow.upload(l_elow.data(), l_elow.size(), st);
+    if (!rc) rc = e->d_lgf.upload(l_gf.data(), l_gf.size(), st);
+    if (!rc) rc = e->d_gwn.upload(g_wn.data(), g_wn.size(), st);
+    if (!rc) rc = e->d_giown.upload(g_iown.data(), g_iown.size(), st);
+    if (!rc) rc = e->d_gstart.upload(g_start.data(), g_start.size(), st);
+    if (!rc) rc = e->d_giso.upload(g_iso.data(), g_iso.size(), st);
+    if (!rc) rc = e->d_gbin.upload(gbin.data(), gbin.size(), st);
+    if (rc) return rc;
+    PB_CUDA(cudaStreamSynchronize(st));
+    e->n_inwin = (int64_t)l_wn.size();
+    e->ngroups = ngroups;
+    e->nadd = nadd;
+    e->nbins = nbins;
+    e->binw = binw;
+    e->has_lines = true;
+    return 0;
+}
+
+int pb200_engine_line_stats(const pb200_engine *e, int64_t stats[3]) {
+    if (!e || !stats) return fail(PB200_EINVAL, "pb200_engine_line_stats: null argument");
+    if (!e->has_lines) return fail(PB200_ESTATE, "pb200_engine_line_stats: no lines loaded");
+    stats[0] = e->n_inwin;
+    stats[1] = e->ngroups;
+    stats[2] = e->nadd;
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------
+static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
+                     const double *unit_density, const double *unit_isoz,
+                     const int64_t *iso_iext, int nextinct, double ethresh, int add,
+                     int resolution, double *out_host, double *out_dev, int64_t *counters,
+                     cudaStream_t user_stream) {
+    if (!e || n_units < 0 || !unit_temp || !unit_density || !iso_iext || nextinct < 1)
+        return fail(PB200_EINVAL, "pb200_extinction_batch: null or empty argument");
+    if (!e->has_grid || !e->has_voigt || !e->has_species || !e->has_lines)
+        return fail(PB200_ESTATE, "pb200_extinction_batch: engine needs grid, voigt, species "
+                                  "and lines before a batch call");
+    if (!unit_isoz && e->pf_ntemp == 0)
+        return fail(PB200_EINVAL, "pb200_extinction_batch: unit_isoz is NULL and no partition "
+                                  "tables were set");
+    if (!out_host && !out_dev) return fail(PB200_EINVAL, "pb200_extinction_batch: null output");
+    PB_CUDA(cudaSetDevice(e->device));
+    if (n_units == 0) return 0;
+    cudaStream_t st = e->stream;
+    const int niso = e->niso, nmol = e->nmol, nlor = e->nlor, ndop = e->ndop;
+    const int nrows = add ? 1 : nextinct;
+    const int64_t nwave = e->nwave, onwn = e->onwn;
+    const double own0 = e->own[0];
+    const double ownstep = e->own[1] - e->own[0];  // :186
+    const double wnstep = e->wn[1] - e->wn[0];     // :185
+    const double cutoff = e->cutoff;
+
+    // Output row of every isotope (iso_iext, :209-212,234-237).
+    std::vector<int> iso_row(niso);
+    for (int i = 0; i < niso; i++) {
+        if (iso_iext[i] >= nextinct)
+            return fail(PB200_EINVAL, "pb200_extinction_batch: iso_iext >= nextinct");
+        iso_row[i] = iso_iext[i] < 0 ? -1 : (add ? 0 : (int)iso_iext[i]);
+    }
+
+    // Partition functions when the caller leaves them to the engine.
+    std::vector<double> isoz_local;
+    if (!unit_isoz) {
+        isoz_local.resize((size_t)n_units * niso);
+        const double *tg = e->pf_temp.data();
+        const int nt = e->pf_ntemp;
+        for (int u = 0; u < n_units; u++) {
+            const double t = unit_temp[u];
+            if (!(t >= tg[0] && t <= tg[nt - 1]))
+                return fail(PB200_EINVAL, "pb200_extinction_batch: temperature outside the "
+                                          "partition-function table");
+            int lo = (int)(std::upper_bound(tg, tg + nt, t) - tg) - 1;
+            if (lo > nt - 2) lo = nt - 2;
+            const double f = (t - tg[lo]) / (tg[lo + 1] - tg[lo]);
+            for (int i = 0; i < niso; i++) {
+                const double *z = e->pf_z.data() + (size_t)i * nt;
+                isoz_local[(size_t)u * niso + i] = z[lo] + (z[lo + 1] - z[lo]) * f;
+            }
+        }
+        unit_isoz = isoz_local.data();
+    }
+
+    // Per-unit scalars, exactly as _extcoeff.c:138-200.
+    std::vector<UnitParams> units(n_units);
+    std::vector<IsoUnit> iso_units((size_t)n_units * niso);
+    std::map<std::vector<double>, int> tp_index;
+    std::vector<double> tp_temp, tp_isoz;
+    std::vector<int> unit_tp(n_units);
+    for (int u = 0; u < n_units; u++) {
+        const double temp = unit_temp[u];
+        const double *dens = unit_density + (size_t)u * nmol;
+        const double fdop = std::sqrt(2 * kBoltzmann * temp / kAmu) * kSqrtLn2 / kLightSpeed;
+        const double flor = std::sqrt(2 * kBoltzmann * temp / kPi / kAmu) / kLightSpeed;
+        double minwidth = 1e5;
+        for (int i = 0; i < niso; i++) {
+            const int imol = e->iso_imol[i];
+            double al = 0.0;
+            for (int j = 0; j < nmol; j++) {
+                const double cd = e->mol_radius[imol] + e->mol_radius[j];
+                al += dens[j] * cd * cd * std::sqrt(1 / e->iso_mass[i] + 1 / e->mol_mass[j]);
+            }
+            al *= flor;
+            const double ad = fdop / std::sqrt(e->iso_mass[i]);
+            const double dw = ad * own0;
+            const double vw = 0.5346 * al + std::sqrt(al * al * 0.2166 + dw * dw);
+            minwidth = std::fmin(minwidth, vw);
+            IsoUnit &I = iso_units[(size_t)u * niso + i];
+            I.adop = ad;
+            I.dens = add ? dens[imol] : 1.0;
+            I.ilor = nearest_bisect(e->lorentz.data(), al, 0, nlor - 1);
+        }
+        int d;
+        const int ndivs = (int)e->divisors.size();
+        for (d = 1; d < ndivs; d++)
+            if (e->divisors[d] * ownstep >= 0.5 * minwidth) break;
+        const int ofactor = (int)e->divisors[d - 1];
+        UnitParams &U = units[u];
+        U.ofactor = ofactor;
+        U.dwnstep = ownstep * ofactor;
+        U.dnwn = (int)(1 + (onwn - 1) / ofactor);
+        U.cut_steps = cutoff / U.dwnstep;
+        U.scale = (int)std::round(wnstep / ownstep / ofactor);
+        if (U.scale < 1) U.scale = 1;
+        U.mcount = 1 + (U.dnwn - 1) / U.scale;
+        if (U.mcount > nwave) U.mcount = (int)nwave;
+        U.out_index = u;
+        for (int i = 0; i < niso; i++) {
+            IsoUnit &I = iso_units[(size_t)u * niso + i];
+            int pmax = 0;
+            for (int n = 0; n < ndop; n++) pmax = std::max(pmax, e->psize[(size_t)I.ilor * ndop + n]);
+            long long reach = pmax;
+            if (cutoff > 0.0) reach = std::min<long long>(reach, (long long)(cutoff / ownstep) + 1);
+            reach += 2LL * ofactor + 2;
+            I.reach = (int)std::min<long long>(reach, 0x7fffffffLL);
+        }
+        // distinct (T, Z) -> strengths pass
+        std::vector<double> key(1 + niso);
+        key[0] = temp;
+        for (int i = 0; i < niso; i++) key[1 + i] = unit_isoz[(size_t)u * niso + i];
+        auto it = tp_index.find(key);
+        if (it == tp_index.end()) {
+            const int id = (int)tp_temp.size();
+            tp_index.emplace(key, id);
+            tp_temp.push_back(temp);
+            tp_isoz.insert(tp_isoz.end(), key.begin() + 1, key.end());
+            unit_tp[u] = id;
+        } else {
+            unit_tp[u] = it->second;
+        }
+    }
+    const int ntp = (int)tp_temp.size();
+
+    // Output buffer first, then chunk the strengths passes so that ksum[ntp_chunk, ngroups]
+    // fits in 60% of what is left.
+    int rc = 0;
+    const size_t out_bytes = sizeof(double) * (size_t)n_units * nrows * (size_t)nwave;
+    double *d_out = out_dev;
+    if (!out_dev) {
+        rc = e->d_out.alloc((size_t)n_units * nrows * (size_t)nwave);
+        if (rc) return rc;
+        d_out = e->d_out.p;
+    }
+    size_t free_b = 0, total_b = 0;
+    PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = (size_t)(0.6 * (double)(free_b + sizeof(double) * e->d_ksum.n));
+    const size_t per_tp = sizeof(double) * (size_t)std::max<int64_t>(e->ngroups, 1);
+    int tp_chunk = (int)std::min<size_t>((size_t)ntp, std::max<size_t>(1, budget / per_tp));
+    if (tp_chunk > 65535) tp_chunk = 65535;
+
+    rc = e->d_ksum.alloc((size_t)tp_chunk * (size_t)std::max<int64_t>(e->ngroups, 1));
+    if (!rc) rc = e->d_kmax.alloc((size_t)tp_chunk * nrows);
+    if (!rc) rc = e->d_tp_temp.alloc(tp_chunk);
+    if (!rc) rc = e->d_tp_isoz.alloc((size_t)tp_chunk * niso);
+    if (!rc) rc = e->d_units.alloc(n_units);
+    if (!rc) rc = e->d_iso_units.alloc((size_t)n_units * niso);
+    if (!rc) rc = e->d_iso_row.alloc(niso);
+    if (!rc && counters) rc = e->d_counters.alloc((size_t)n_units * 4);
+    if (rc) return rc;
+
+    if (user_stream) {
+        // order after work already queued on the caller's stream
+        PB_CUDA(cudaEventRecord(e->ev[5], user_stream));
+        PB_CUDA(cudaStreamWaitEvent(st, e->ev[5], 0));
+    }
+    PB_CUDA(cudaEventRecord(e->ev[0], st));
+    PB_CUDA(cudaMemcpyAsync(e->d_iso_row.p, iso_row.data(), sizeof(int) * niso,
+                            cudaMemcpyHostToDevice, st));
+    if (counters) PB_CUDA(cudaMemsetAsync(e->d_counters.p, 0, sizeof(unsigned long long) * n_units * 4, st));
+
+    const StaticView V = e->view();
+    float ms_strengths = 0.f, ms_accum = 0.f;
+    // order units by strengths pass
+    std::vector<int> order(n_units);
+    for (int u = 0; u < n_units; u++) order[u] = u;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return unit_tp[a] < unit_tp[b]; });
+    size_t pos = 0;
+    for (int tp0 = 0; tp0 < ntp; tp0 += tp_chunk) {
+        const int ntc = std::min(tp_chunk, ntp - tp0);
+        std::vector<UnitParams> cu;
+        std::vector<IsoUnit> ci;
+        while (pos < order.size() && unit_tp[order[pos]] < tp0 + ntc) {
+            const int u = order[pos++];
+            UnitParams U = units[u];
+            U.tpass = unit_tp[u] - tp0;
+            cu.push_back(U);
+            ci.insert(ci.end(), iso_units.begin() + (size_t)u * niso,
+                      iso_units.begin() + (size_t)(u + 1) * niso);
+        }
+        PB_CUDA(cudaMemcpyAsync(e->d_tp_temp.p, tp_temp.data() + tp0, sizeof(double) * ntc,
+                                cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(e->d_tp_isoz.p, tp_isoz.data() + (size_t)tp0 * niso,
+                                sizeof(double) * ntc * niso, cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(e->d_units.p, cu.data(), sizeof(UnitParams) * cu.size(),
+                                cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemcpyAsync(e->d_iso_units.p, ci.data(), sizeof(IsoUnit) * ci.size(),
+                                cudaMemcpyHostToDevice, st));
+        PB_CUDA(cudaMemsetAsync(e->d_kmax.p, 0, sizeof(unsigned long long) * ntc * nrows, st));
+        PB_CUDA(cudaEventRecord(e->ev[1], st));
+        rc = launch_strengths(st, V, ntc, e->d_tp_temp.p, e->d_tp_isoz.p, e->d_iso_row.p, nrows,
+                              e->d_ksum.p, e->d_kmax.p);
+        if (rc) return rc;
+        if (V.ngroups > 0) e->launches++;
+        PB_CUDA(cudaEventRecord(e->ev[2], st));
+        // grid.y is limited to 65535 units per launch
+        for (size_t u0 = 0; u0 < cu.size(); u0 += 65535) {
+            const int nu = (int)std::min<size_t>(65535, cu.size() - u0);
+            rc = launch_accumulate(st, V, nu, e->d_units.p + u0, e->d_iso_units.p + u0 * niso,
+                                   e->d_iso_row.p, e->d_ksum.p, e->d_kmax.p, nrows, ethresh,
+                                   cutoff, resolution ? 1 : 0, d_out);
+            if (rc) return rc;
+            e->launches++;
+            if (counters) {
+                rc = launch_counters(st, V, nu, e->d_units.p + u0, e->d_iso_units.p + u0 * niso,
+                                     e->d_iso_row.p, e->d_ksum.p, e->d_kmax.p, nrows, ethresh,
+                                     cutoff, resolution ? 1 : 0, e->d_counters.p);
+                if (rc) return rc;
+                if (V.ngroups > 0) e->launches++;
+            }
+        }
+        PB_CUDA(cudaEventRecord(e->ev[3], st));
+        // the host vectors cu/ci must stay alive until their copies have completed
+        PB_CUDA(cudaStreamSynchronize(st));
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, e->ev[1], e->ev[2]);
+        cudaEventElapsedTime(&b, e->ev[2], e->ev[3]);
+        ms_strengths += a;
+        ms_accum += b;
+    }
+    PB_CUDA(cudaEventRecord(e->ev[3], st));
+    if (out_host)
+        PB_CUDA(cudaMemcpyAsync(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    std::vector<unsigned long long> cnt;
+    if (counters) {
+        cnt.resize((size_t)n_units * 4);
+        PB_CUDA(cudaMemcpyAsync(cnt.data(), e->d_counters.p, sizeof(unsigned long long) * cnt.size(),
+                                cudaMemcpyDeviceToHost, st));
+    }
+    PB_CUDA(cudaEventRecord(e->ev[4], st));
+    if (user_stream && out_dev) {
+        PB_CUDA(cudaStreamWaitEvent(user_stream, e->ev[4], 0));
+    }
+    PB_CUDA(cudaStreamSynchronize(st));
+    if (counters) {
+        // nadd is static per isotope: lines absorbed into a head line of a processed isotope
+        int64_t nadd = 0;
+        for (int i = 0; i < niso; i++)
+            if (iso_row[i] >= 0) nadd += e->iso_nadd[i];
+        for (int u = 0; u < n_units; u++) {
+            counters[(size_t)u * 5 + 0] = nadd;
+            counters[(size_t)u * 5 + 1] = (int64_t)cnt[(size_t)u * 4 + 0];
+            counters[(size_t)u * 5 + 2] = (int64_t)cnt[(size_t)u * 4 + 1];
+            counters[(size_t)u * 5 + 3] = (int64_t)cnt[(size_t)u * 4 + 2];
+            counters[(size_t)u * 5 + 4] = (int64_t)cnt[(size_t)u * 4 + 3];
+        }
+    }
+    float t_all = 0.f, t_d2h = 0.f;
+    cudaEventElapsedTime(&t_all, e->ev[0], e->ev[4]);
+    cudaEventElapsedTime(&t_d2h, e->ev[3], e->ev[4]);
+    e->timing[0] = ms_strengths;
+    e->timing[1] = ms_accum;
+    e->timing[2] = t_all - ms_strengths - ms_accum - t_d2h;
+    e->timing[3] = t_d2h;
+    e->timing[4] = t_all;
+    return 0;
+}
+
+int pb200_extinction_batch_host(pb200_engine *e, int n_units, const double *unit_temp,
+                                const double *unit_density, const double *unit_isoz,
+                                const int64_t *iso_iext, int nextinct, double ethresh, int add,
+                                int resolution, double *out, int64_t *counters) {
+    if (!out) return fail(PB200_EINVAL, "pb200_extinction_batch_host: null output");
+    return run_batch(e, n_units, unit_temp, unit_density, unit_isoz, iso_iext, nextinct,
+                     ethresh, add, resolution, out, nullptr, counters, nullptr);
+}
+
+int pb200_extinction_batch_dev(pb200_engine *e, int n_units, const double *unit_temp,
+                               const double *unit_density, const double *unit_isoz,
+                               const int64_t *iso_iext, int nextinct, double ethresh, int add,
+                               int resolution, double *out_dev, int64_t *counters,
+                               void *cuda_stream) {
+    if (!out_dev) return fail(PB200_EINVAL, "pb200_extinction_batch_dev: null output");
+    return run_batch(e, n_units, unit_temp, unit_density, unit_isoz, iso_iext, nextinct,
+                     ethresh, add, resolution, nullptr, out_dev, counters,
+                     (cudaStream_t)cuda_stream);
+}
+
+int pb200_engine_last_timing(const pb200_engine *e, double ms[5]) {
+    if (!e || !ms) return fail(PB200_EINVAL, "pb200_engine_last_timing: null argument");
+    for (int i = 0; i < 5; i++) ms[i] = e->timing[i];
+    return 0;
+}
+
+int64_t pb200_engine_launch_count(const pb200_engine *e) { return e ? e->launches : 0; }
+
+// ----------------------------------------------------------------------------------------
+static int interp_impl(int device, double *ext, const double *etable, bool on_device,
+                       const double *ttable, const double *temperature, const double *density,
+                       int nspec, int ntemp, int nlayers, int nwave, int lay1, int lay2,
+                       int per_mol, cudaStream_t user_stream) {
+    if (!ext || !etable || !ttable || !temperature || !density || nspec < 1 || ntemp < 2 ||
+        nlayers < 1 || nwave < 1)
+        return fail(PB200_EINVAL, "pb200_interp_ec: null argument or ntemp<2");
+    int rc = select_device(device);
+    if (rc) return rc;
+    if (lay2 > nlayers) lay2 = nlayers;  // :389
+    if (lay1 < 0) return fail(PB200_EINVAL, "pb200_interp_ec: lay1 < 0");
+    if (lay2 <= lay1) return 0;
+    // Host: bracketing temperature and weights per layer (:392-402)
+    std::vector<int> tlo(nlayers, 0);
+    std::vector<double> w_lo(nlayers, 0.0), w_hi(nlayers, 0.0);
+    for (int k = lay1; k < lay2; k++) {
+        const double t = temperature[k];
+        int lo = nearest_bisect(ttable, t, 0, ntemp - 1);
+        if (t < ttable[lo] || lo == ntemp - 1) lo--;
+        if (lo < 0) lo = 0;  // the reference would index ttable[-1]; clamp instead
+        const int hi = lo + 1;
+        tlo[k] = lo;
+        w_lo[k] = (ttable[hi] - t) / (ttable[hi] - ttable[lo]);
+        w_hi[k] = (t - ttable[lo]) / (ttable[hi] - ttable[lo]);
+    }
+    cudaStream_t st = user_stream;
+    bool own_stream = false;
+    if (!st) {
+        PB_CUDA(cudaStreamCreate(&st));
+        own_stream = true;
+    }
+    DevBuf<int> d_tlo;
+    DevBuf<double> d_wlo, d_whi, d_dens, d_tab, d_ext;
+    const size_t tab_n = (size_t)nspec * ntemp * nlayers * (size_t)nwave;
+    const size_t ext_n = (size_t)(per_mol ? nspec : 1) * nlayers * (size_t)nwave;
+    rc = d_tlo.upload(tlo.data(), nlayers, st);
+    if (!rc) rc = d_wlo.upload(w_lo.data(), nlayers, st);
+    if (!rc) rc = d_whi.upload(w_hi.data(), nlayers, st);
+    if (!rc) rc = d_dens.upload(density, (size_t)nlayers * nspec, st);
+    const double *tab = etable;
+    double *dext = ext;
+    if (!on_device) {
+        if (!rc) rc = d_tab.upload(etable, tab_n, st);
+        if (!rc) rc = d_ext.upload(ext, ext_n, st);
+        tab = d_tab.p;
+        dext = d_ext.p;
+    }
+    if (!rc)
+        rc = launch_interp_ec(st, dext, tab, d_tlo.p, d_wlo.p, d_whi.p, d_dens.p, nspec, ntemp,
+                              nlayers, nwave, lay1, lay2, per_mol);
+    if (!rc && !on_device) {
+        cudaError_t e2 = cudaMemcpyAsync(ext, dext, sizeof(double) * ext_n,
+                                         cudaMemcpyDeviceToHost, st);
+        if (e2 != cudaSuccess) rc = cuda_fail(e2, "interp d2h", __FILE__, __LINE__);
+    }
+    cudaError_t e3 = cudaStreamSynchronize(st);
+    if (!rc && e3 != cudaSuccess) rc = cuda_fail(e3, "interp sync", __FILE__, __LINE__);
+    if (own_stream) cudaStreamDestroy(st);
+    return rc;
+}
+
+int pb200_interp_ec(int device, double *ext, const double *etable, const double *ttable,
+                    const double *temperature, const double *density, int nspec, int ntemp,
+                    int nlayers, int nwave, int lay1, int lay2) {
+    return interp_impl(device, ext, etable, false, ttable, temperature, density, nspec, ntemp,
+                       nlayers, nwave, lay1, lay2, 0, nullptr);
+}
+
+int pb200_interp_ec_per_mol(int device, double *ext, const double *etable,
+                            const double *ttable, const double *temperature,
+                            const double *density, int nspec, int ntemp, int nlayers, int nwave,
+                            int lay1, int lay2) {
+    return interp_impl(device, ext, etable, false, ttable, temperature, density, nspec, ntemp,
+                       nlayers, nwave, lay1, lay2, 1, nullptr);
+}
+
+int pb200_interp_ec_dev(int device, double *ext_dev, const double *etable_dev,
+                        const double *ttable, const double *temperature, const double *density,
+                        int nspec, int ntemp, int nlayers, int nwave, int lay1, int lay2,
+                        int per_mol, void *cuda_stream) {
+    return interp_impl(device, ext_dev, etable_dev, true, ttable, temperature, density, nspec,
+                       ntemp, nlayers, nwave, lay1, lay2, per_mol, (cudaStream_t)cuda_stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,349 @@
+// lbl_kernels.cu -- strengths, accumulate, counters and table-interpolation kernels.
+//
+// Kernel 1 (strengths_kernel)   _extcoeff.c:203-226 + the group sums of :248-262
+// Kernel 3 (accumulate_kernel)  _extcoeff.c:229-309 + output stage :320-332 (utils.h:119-163)
+// counters_kernel               the verbose counters of _extcoeff.c:311-318
+// interp_ec_kernel              _extcoeff.c:367-472
+//
+// Design (DESIGN.md has the long form): the reference scatters every line onto a dynamic
+// fine grid and then keeps 1 of `scale` samples (resample) or 2 per output point (linterp).
+// Here each thread OWNS one output sample, visits the co-add groups whose footprint covers
+// it and gathers exactly the profile samples the reference would have left in that output:
+// no atomics, no scratch spectrum, accumulation in a register.  Groups are prepared
+// (ethresh test, nearest Doppler profile, index range) 32 at a time, one per lane, staged in
+// shared memory and then broadcast to the warp.
+#include "lbl_kernels.cuh"
+
+#include <climits>
+
+namespace pb200 {
+
+struct Prep {
+    double k;
+    long long base;  // profile index of dynamic sample j is base + ofactor*j
+    int jlo, jhi;    // dynamic-sample range [jlo, jhi)
+};
+
+// The per-group part of _extcoeff.c:264-299, identical integer/floating-point decisions.
+__device__ __forceinline__ bool prepare_group(const StaticView &V, const UnitParams &U,
+                                              const IsoUnit &I, const double *s_doppler,
+                                              double kthr, double cutoff, double w, int iown,
+                                              double k, Prep *out) {
+    if (k < kthr) return false;  // :265 skip weak lines
+    k = dmul(k, I.dens);         // :271-272 (dens == 1 when add == 0)
+    const int idwn = (int)ddiv(dsub(w, V.own0), U.dwnstep);                 // :275
+    const int idop = nearest_index(s_doppler, V.ndop, dmul(I.adop, w));     // :278
+    const int at = I.ilor * V.ndop + idop;
+    const int half = V.psize[at];
+    const int sub = iown - idwn * U.ofactor;                                // :281
+    int jlo = idwn - (half - sub) / U.ofactor;                              // :286
+    int jhi = idwn + (half + sub) / U.ofactor;                              // :287
+    if (jlo < 0) jlo = 0;
+    if (jhi > U.dnwn) jhi = U.dnwn;
+    if (cutoff > 0.0) {                                                     // :294-299
+        const int lo_cut = (int)dsub((double)idwn, U.cut_steps);
+        const int hi_cut = (int)dadd((double)idwn, U.cut_steps);
+        if (lo_cut > jlo) jlo = lo_cut;
+        if (hi_cut < jhi) jhi = hi_cut;
+    }
+    out->k = k;
+    out->base = V.pindex[at] + (long long)half - (long long)iown;           // :283,303
+    out->jlo = jlo;
+    out->jhi = jhi;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel 1: line strengths per (T, Z) pass, summed per co-add group, and the per-row maximum.
+__global__ void __launch_bounds__(256)
+strengths_kernel(StaticView V, const double *__restrict__ tp_temp,
+                 const double *__restrict__ tp_isoz, const int *__restrict__ iso_row,
+                 int nrows, double *__restrict__ ksum,
+                 unsigned long long *__restrict__ kmax) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int tp = blockIdx.y;
+    double best = 0.0;
+    int row = -1;
+    if (g < V.ngroups) {
+        const int iso = V.g_iso[g];
+        row = iso_row[iso];
+        double k = 0.0;
+        if (row >= 0) {
+            const double temp = tp_temp[tp];
+            const double z = tp_isoz[(size_t)tp * V.niso + iso];
+            const double pref = dmul(kSigCte, V.iso_ratio[iso]);
+            const unsigned int s = V.g_start[g], e = V.g_start[g + 1];
+            for (unsigned int ln = s; ln < e; ln++) {
+                const double w = V.l_wn[ln];
+                // SIGCTE*ratio*gf * exp(-EXPCTE*elow/T) * (1-exp(-EXPCTE*wn/T)) / Z   (:219-224)
+                const double pop = exp(ddiv(dmul(-kExpCte, V.l_elow[ln]), temp));
+                const double ind = dsub(1.0, exp(ddiv(dmul(-kExpCte, w), temp)));
+                const double kl = ddiv(dmul(dmul(dmul(pref, V.l_gf[ln]), pop), ind), z);
+                k = (ln == s) ? kl : dadd(k, kl);  // :248,258 sequential co-add
+                best = fmax(best, kl);             // :225 maximum over single lines
+            }
+        }
+        ksum[(size_t)tp * V.ngroups + g] = k;
+    }
+    // kprop >= 0, so the IEEE bit pattern orders like the value.
+    if (nrows == 1) {
+        for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+        __shared__ double s_best[8];
+        if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < 8; i++) best = fmax(best, s_best[i]);
+            if (best > 0.0)
+                atomicMax(&kmax[tp], (unsigned long long)__double_as_longlong(best));
+        }
+    } else if (row >= 0 && best > 0.0) {
+        atomicMax(&kmax[(size_t)tp * nrows + row],
+                  (unsigned long long)__double_as_longlong(best));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel 3: output-owned accumulation.  grid = (tiles, units, rows), 256 threads.
+template <bool LINTERP>
+__global__ void __launch_bounds__(256)
+accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
+                  const IsoUnit *__restrict__ iso_units, const int *__restrict__ iso_row,
+                  const double *__restrict__ ksum,
+                  const unsigned long long *__restrict__ kmax, int nrows, double ethresh,
+                  double cutoff, double *__restrict__ out) {
+    extern __shared__ double s_doppler[];  // [ndop]
+    __shared__ double s_k[8][32];
+    __shared__ long long s_base[8][32];
+    __shared__ int2 s_j[8][32];
+
+    for (int i = threadIdx.x; i < V.ndop; i += blockDim.x) s_doppler[i] = V.doppler[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const UnitParams U = units[blockIdx.y];
+    const int row = blockIdx.z;
+    const int m = blockIdx.x * kTileOutputs + threadIdx.x;
+    const bool in_grid = m < V.nwave;
+
+    // Dynamic samples this output needs: one (resample, utils.h:132) or two (linterp, :153-160).
+    int j0 = -1, j1 = -1;
+    double wn_i = 0.0;
+    if (LINTERP) {
+        if (in_grid) {
+            wn_i = V.wn[m];
+            j0 = (int)ddiv(dsub(wn_i, V.wn0), U.dwnstep);
+            j1 = j0 + 1;
+        }
+    } else if (in_grid && m < U.mcount) {
+        j0 = U.scale * m;
+    }
+    int jmin = (j0 >= 0) ? j0 : INT_MAX;
+    int jmax = (j0 >= 0) ? (LINTERP ? j1 : j0) : INT_MIN;
+    jmin = __reduce_min_sync(0xffffffffu, jmin);
+    jmax = __reduce_max_sync(0xffffffffu, jmax);
+
+    double acc0 = 0.0, acc1 = 0.0;
+    if (jmax >= jmin) {
+        const double *__restrict__ ks = ksum + (size_t)U.tpass * V.ngroups;
+        for (int iso = 0; iso < V.niso; iso++) {
+            if (iso_row[iso] != row) continue;
+            const IsoUnit I = iso_units[(size_t)blockIdx.y * V.niso + iso];
+            long long flo = (long long)jmin * U.ofactor - I.reach;
+            long long fhi = (long long)jmax * U.ofactor + I.reach;
+            if (fhi < 0 || flo > V.onwn - 1) continue;
+            if (flo < 0) flo = 0;
+            if (fhi > V.onwn - 1) fhi = V.onwn - 1;
+            const int *gb = V.gbin + (size_t)iso * (V.nbins + 1);
+            const int glo = gb[(int)(flo / V.binw)];
+            const int ghi = gb[(int)(fhi / V.binw) + 1];
+            const double kthr =
+                dmul(ethresh, __longlong_as_double((long long)kmax[(size_t)U.tpass * nrows + row]));
+            for (int c = glo; c < ghi; c += 32) {
+                const int g = c + lane;
+                Prep p;
+                p.k = 0.0; p.base = 0; p.jlo = 0; p.jhi = 0;
+                if (g < ghi)
+                    prepare_group(V, U, I, s_doppler, kthr, cutoff, V.g_wn[g], V.g_iown[g],
+                                  ks[g], &p);
+                s_k[warp][lane] = p.k;
+                s_base[warp][lane] = p.base;
+                s_j[warp][lane] = make_int2(p.jlo, p.jhi);
+                __syncwarp();
+                const int n = min(32, ghi - c);
+                for (int t = 0; t < n; t++) {
+                    const int2 jr = s_j[warp][t];
+                    if (jr.y <= jmin || jr.x > jmax) continue;  // warp-uniform
+                    const double k = s_k[warp][t];
+                    const long long base = s_base[warp][t];
+                    if (j0 >= jr.x && j0 < jr.y)
+                        acc0 = fma(k, __ldg(V.profile + base + (long long)U.ofactor * j0), acc0);
+                    if (LINTERP && j1 >= jr.x && j1 < jr.y)
+                        acc1 = fma(k, __ldg(V.profile + base + (long long)U.ofactor * j1), acc1);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    if (in_grid) {
+        double *dst = out + ((size_t)U.out_index * nrows + row) * (size_t)V.nwave;
+        if (LINTERP) {
+            const double wlo = dadd(V.wn0, dmul(U.dwnstep, (double)j0));
+            dst[m] = (acc0 * (wlo + U.dwnstep - wn_i) + acc1 * (wn_i - wlo)) / U.dwnstep;
+        } else {
+            dst[m] = acc0;  // 0 beyond mcount
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Counters: nskip, neval, dynamic samples (reference-equivalent work) and samples gathered.
+__global__ void __launch_bounds__(256)
+counters_kernel(StaticView V, const UnitParams *__restrict__ units,
+                const IsoUnit *__restrict__ iso_units, const int *__restrict__ iso_row,
+                const double *__restrict__ ksum, const unsigned long long *__restrict__ kmax,
+                int nrows, double ethresh, double cutoff, int linterp,
+                unsigned long long *__restrict__ counters /* [units,4] */) {
+    extern __shared__ double s_doppler[];
+    for (int i = threadIdx.x; i < V.ndop; i += blockDim.x) s_doppler[i] = V.doppler[i];
+    __syncthreads();
+    const UnitParams U = units[blockIdx.y];
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long skip = 0, eval = 0, dyn = 0, used = 0;
+    if (g < V.ngroups) {
+        const int iso = V.g_iso[g];
+        const int row = iso_row[iso];
+        if (row >= 0) {
+            const IsoUnit I = iso_units[(size_t)blockIdx.y * V.niso + iso];
+            const double kthr =
+                dmul(ethresh, __longlong_as_double((long long)kmax[(size_t)U.tpass * nrows + row]));
+            Prep p;
+            if (prepare_group(V, U, I, s_doppler, kthr, cutoff, V.g_wn[g], V.g_iown[g],
+                              ksum[(size_t)U.tpass * V.ngroups + g], &p)) {
+                eval = 1;
+                if (p.jhi > p.jlo) {
+                    dyn = (unsigned long long)(p.jhi - p.jlo);
+                    if (!linterp) {
+                        // outputs m < mcount with scale*m in [jlo, jhi)
+                        long long mlo = ((long long)p.jlo + U.scale - 1) / U.scale;
+                        long long mhi = ((long long)p.jhi + U.scale - 1) / U.scale;
+                        if (mhi > U.mcount) mhi = U.mcount;
+                        if (mhi > V.nwave) mhi = V.nwave;
+                        if (mhi > mlo) used = (unsigned long long)(mhi - mlo);
+                    } else {
+                        // outputs whose bracketing pair (ilo, ilo+1) touches [jlo, jhi): counted
+                        // on the output grid by bisection; each touching output gathers <= 2.
+                        const double a = dadd(V.wn0, dmul(U.dwnstep, (double)(p.jlo - 1)));
+                        const double b = dadd(V.wn0, dmul(U.dwnstep, (double)p.jhi));
+                        int lo = 0, hi = V.nwave;
+                        while (lo < hi) { int mid = (lo + hi) >> 1; if (V.wn[mid] < a) lo = mid + 1; else hi = mid; }
+                        const int first = lo;
+                        hi = V.nwave;
+                        while (lo < hi) { int mid = (lo + hi) >> 1; if (V.wn[mid] < b) lo = mid + 1; else hi = mid; }
+                        used = 2ull * (unsigned long long)(lo - first);
+                    }
+                }
+            } else {
+                skip = 1;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        skip += __shfl_xor_sync(0xffffffffu, skip, o);
+        eval += __shfl_xor_sync(0xffffffffu, eval, o);
+        dyn += __shfl_xor_sync(0xffffffffu, dyn, o);
+        used += __shfl_xor_sync(0xffffffffu, used, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long *c = counters + (size_t)U.out_index * 4;
+        if (skip) atomicAdd(&c[0], skip);
+        if (eval) atomicAdd(&c[1], eval);
+        if (dyn) atomicAdd(&c[2], dyn);
+        if (used) atomicAdd(&c[3], used);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Table interpolation in temperature.  grid = (wave chunks, layers); bit-exact with the
+// reference's operation order: ext += (tab_lo*e1 + tab_hi*e2) for each species in turn.
+__global__ void __launch_bounds__(256)
+interp_ec_kernel(double *__restrict__ ext, const double *__restrict__ table,
+                 const int *__restrict__ tlo, const double *__restrict__ w_lo,
+                 const double *__restrict__ w_hi, const double *__restrict__ density,
+                 int nspec, int ntemp, int nlayers, int nwave, int lay1, int per_mol) {
+    const int k = lay1 + blockIdx.y;
+    const int lo = tlo[k];
+    const double wl = w_lo[k], wh = w_hi[k];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwave; i += gridDim.x * blockDim.x) {
+        double acc = per_mol ? 0.0 : ext[(size_t)k * nwave + i];
+        for (int j = 0; j < nspec; j++) {
+            const double d = density[(size_t)k * nspec + j];
+            const double e1 = dmul(wl, d), e2 = dmul(wh, d);
+            const double *r = table + (((size_t)j * ntemp + lo) * nlayers + k) * (size_t)nwave + i;
+            const double v = dadd(dmul(r[0], e1), dmul(r[(size_t)nlayers * nwave], e2));
+            if (per_mol) {
+                double *dst = ext + ((size_t)j * nlayers + k) * (size_t)nwave + i;
+                *dst = dadd(*dst, v);
+            } else {
+                acc = dadd(acc, v);
+            }
+        }
+        if (!per_mol) ext[(size_t)k * nwave + i] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Launch wrappers
+int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double *tp_temp,
+                     const double *tp_isoz, const int *iso_row, int nrows, double *ksum,
+                     unsigned long long *kmax) {
+    if (V.ngroups == 0 || ntp == 0) return 0;
+    dim3 grid((unsigned)((V.ngroups + 255) / 256), (unsigned)ntp);
+    strengths_kernel<<<grid, 256, 0, st>>>(V, tp_temp, tp_isoz, iso_row, nrows, ksum, kmax);
+    PB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
+                      const UnitParams *units, const IsoUnit *iso_units, const int *iso_row,
+                      const double *ksum, const unsigned long long *kmax, int nrows,
+                      double ethresh, double cutoff, int linterp, double *out) {
+    if (nunits == 0 || V.nwave == 0) return 0;
+    dim3 grid((unsigned)((V.nwave + kTileOutputs - 1) / kTileOutputs), (unsigned)nunits,
+              (unsigned)nrows);
+    const size_t smem = sizeof(double) * V.ndop;
+    if (linterp)
+        accumulate_kernel<true><<<grid, 256, smem, st>>>(V, units, iso_units, iso_row, ksum,
+                                                         kmax, nrows, ethresh, cutoff, out);
+    else
+        accumulate_kernel<false><<<grid, 256, smem, st>>>(V, units, iso_units, iso_row, ksum,
+                                                          kmax, nrows, ethresh, cutoff, out);
+    PB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_counters(cudaStream_t st, const StaticView &V, int nunits, const UnitParams *units,
+                    const IsoUnit *iso_units, const int *iso_row, const double *ksum,
+                    const unsigned long long *kmax, int nrows, double ethresh, double cutoff,
+                    int linterp, unsigned long long *counters) {
+    if (nunits == 0 || V.ngroups == 0) return 0;
+    dim3 grid((unsigned)((V.ngroups + 255) / 256), (unsigned)nunits);
+    counters_kernel<<<grid, 256, sizeof(double) * V.ndop, st>>>(
+        V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, linterp, counters);
+    PB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_interp_ec(cudaStream_t st, double *ext, const double *table, const int *tlo,
+                     const double *w_lo, const double *w_hi, const double *density, int nspec,
+                     int ntemp, int nlayers, int nwave, int lay1, int lay2, int per_mol) {
+    if (lay2 <= lay1 || nwave == 0) return 0;
+    int bx = (nwave + 255) / 256;
+    if (bx > 1024) bx = 1024;
+    dim3 grid((unsigned)bx, (unsigned)(lay2 - lay1));
+    interp_ec_kernel<<<grid, 256, 0, st>>>(ext, table, tlo, w_lo, w_hi, density, nspec, ntemp,
+                                           nlayers, nwave, lay1, per_mol);
+    PB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace pb200

@@ -1,0 +1,25 @@
+// lbl_kernels.cuh -- launch wrappers of the line-by-line kernels (lbl_kernels.cu).
+#pragma once
+#include "engine.cuh"
+
+namespace pb200 {
+
+int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double *tp_temp,
+                     const double *tp_isoz, const int *iso_row, int nrows, double *ksum,
+                     unsigned long long *kmax);
+
+int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
+                      const UnitParams *units, const IsoUnit *iso_units, const int *iso_row,
+                      const double *ksum, const unsigned long long *kmax, int nrows,
+                      double ethresh, double cutoff, int linterp, double *out);
+
+int launch_counters(cudaStream_t st, const StaticView &V, int nunits, const UnitParams *units,
+                    const IsoUnit *iso_units, const int *iso_row, const double *ksum,
+                    const unsigned long long *kmax, int nrows, double ethresh, double cutoff,
+                    int linterp, unsigned long long *counters);
+
+int launch_interp_ec(cudaStream_t st, double *ext, const double *table, const int *tlo,
+                     const double *w_lo, const double *w_hi, const double *density, int nspec,
+                     int ntemp, int nlayers, int nwave, int lay1, int lay2, int per_mol);
+
+}  // namespace pb200
