@@ -146,6 +146,13 @@ int pb200_extinction_batch_dev(pb200_engine *e, int n_units, const double *unit_
 int pb200_engine_last_timing(const pb200_engine *e, double ms[5]);
 /* Kernel launches issued by this engine since creation. */
 int64_t pb200_engine_launch_count(const pb200_engine *e);
+/* The engine's CUDA stream (cudaStream_t), so a caller can record its own events on it. */
+void *pb200_engine_stream(const pb200_engine *e);
+
+/* Device ceilings for roofline statements (bench.py only): fp64 FMA throughput in TFLOP/s
+ * and read bandwidth (GB/s) of an L2-resident buffer of `mbytes` MiB; best of `reps`. */
+int pb200_bench_fp64(int device, int reps, double *tflops);
+int pb200_bench_l2(int device, int mbytes, int reps, double *gbs);
 
 /* Cross-section table interpolation in temperature ------------------------------------------
  * ext[nlayers,nwave] (or [nspec,nlayers,nwave] for per_mol) is ACCUMULATED (+=) like the

@@ -26,10 +26,14 @@ def pressure(ptop, pbottom, nlayers):
 
 
 def ideal_gas_density(vmr, press_bar, temp):
-    """Number density (molecules cm-3): vmr * p / (k T) with the CODATA k the reference's
-    Python layer uses (pyrat/extinction.py:177)."""
+    """Number density (molecules cm-3), same operation order as the reference's
+    atmosphere/atmosphere.py:662-664 so that atm.d is bit-identical."""
     vmr = np.asarray(vmr, np.double)
-    return vmr * np.expand_dims(np.asarray(press_bar) * pc.bar / (pc.k * np.asarray(temp)), -1)
+    press_bar = np.asarray(press_bar, np.double)
+    temp = np.asarray(temp, np.double)
+    if np.shape(vmr) == np.shape(press_bar):
+        return vmr * (press_bar * pc.bar) / (temp * pc.k)
+    return vmr * np.expand_dims(press_bar / temp, axis=1) * pc.bar / pc.k
 
 
 class Atmosphere:

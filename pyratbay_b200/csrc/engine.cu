@@ -814,6 +814,8 @@ int pb200_engine_last_timing(const pb200_engine *e, double ms[5]) {
 
 int64_t pb200_engine_launch_count(const pb200_engine *e) { return e ? e->launches : 0; }
 
+void *pb200_engine_stream(const pb200_engine *e) { return e ? (void *)e->stream : nullptr; }
+
 // ----------------------------------------------------------------------------------------
 static int interp_impl(int device, double *ext, const double *etable, bool on_device,
                        const double *ttable, const double *temperature, const double *density,

@@ -240,3 +240,18 @@ class Engine:
 
     def launch_count(self):
         return int(self._lib.pb200_engine_launch_count(self._h))
+
+    def stream_ptr(self):
+        """Address of the engine's cudaStream_t (for torch.cuda.ExternalStream)."""
+        return int(self._lib.pb200_engine_stream(self._h) or 0)
+
+
+def device_ceilings(device=0, l2_mbytes=32, reps=3):
+    """Measured fp64-FMA TFLOP/s and L2-resident read GB/s (bench.py roofline denominators)."""
+    lib = _lib.load()
+    _lib.require_device()
+    tf, gb = ctypes.c_double(0.0), ctypes.c_double(0.0)
+    check(lib.pb200_bench_fp64(ctypes.c_int(device), ctypes.c_int(reps), ctypes.byref(tf)))
+    check(lib.pb200_bench_l2(ctypes.c_int(device), ctypes.c_int(l2_mbytes), ctypes.c_int(reps),
+                             ctypes.byref(gb)))
+    return tf.value, gb.value

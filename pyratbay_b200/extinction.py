@@ -9,6 +9,7 @@ import numpy as np
 from . import constants as pc
 from . import io
 from . import parallel
+from ._mem import pinned_zeros
 
 
 def compute_opacity(pyrat):
@@ -69,7 +70,7 @@ def compute_opacity(pyrat):
     ex.nlayers = pyrat.atm.nlayers
 
     log.msg("Calculate cross-sections.", indent=2)
-    ex.etable = np.zeros((ex.ntemp, ex.nlayers, ex.nwave), np.double)
+    ex.etable = pinned_zeros((ex.ntemp, ex.nlayers, ex.nwave))
 
     # One batched GPU call per rank over its share of the (T,p) indices (:108-119)
     n_units = ex.ntemp * ex.nlayers
@@ -130,10 +131,14 @@ def extinction(pyrat, indices, grid=False, add=False, skip_mol=[]):
         log.msg(f"Calculating extinction at {len(indices)} layer(s).", indent=2)
 
     nrows = 1 if add else lbl.nspec
+    # Write straight into the caller-visible array when the batch covers it in order.
     out = None
-    if grid and len(indices) == pyrat.ex.etable.shape[0] * pyrat.ex.etable.shape[1] \
-            and np.array_equal(indices, np.arange(len(indices))) and nrows == 1:
-        out = pyrat.ex.etable.reshape(len(indices), 1, spec.nwave)  # write in place
+    in_order = np.array_equal(indices, np.arange(len(indices)))
+    if grid and in_order and nrows == 1 \
+            and len(indices) == pyrat.ex.etable.shape[0] * pyrat.ex.etable.shape[1]:
+        out = pyrat.ex.etable.reshape(len(indices), 1, spec.nwave)
+    elif add and not grid and in_order and len(indices) == atm.nlayers:
+        out = lbl.ec.reshape(atm.nlayers, 1, spec.nwave)
     result = pyrat.engine.extinction_batch(
         temp, density, iso_pf, iso_mol_indices, lbl.nspec, lbl.ethresh, add, interpolate,
         out=out)
@@ -143,6 +148,7 @@ def extinction(pyrat, indices, grid=False, add=False, skip_mol=[]):
         if out is None:
             pyrat.ex.etable[itemp, ilayer] = result[:, 0]
     elif add:
-        lbl.ec[ilayer] = result[:, 0]
+        if out is None:
+            lbl.ec[ilayer] = result[:, 0]
     else:
         return result[0]

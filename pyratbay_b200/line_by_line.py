@@ -5,6 +5,7 @@ import scipy.interpolate as sip
 
 from . import extinction as ex
 from .tli import read_tli_file
+from ._mem import pinned_zeros
 
 
 class Line_By_Line:
@@ -25,7 +26,7 @@ class Line_By_Line:
         self.isoid = np.array([], int)
         self.nwave = pyrat.spec.nwave
         self.nlayers = pyrat.atm.nlayers
-        self.ec = np.zeros((self.nlayers, self.nwave))
+        self.ec = pinned_zeros((self.nlayers, self.nwave))
 
         # Collect all databases; isotope ids are offset per *file* (line_by_line.py:112-125)
         for tli_file in self.tlifile:

@@ -187,9 +187,6 @@ wl_high  = 1.7 um
 wnstep  = 1.0
 wnosamp = 2160
 voigt_extent = 100.0
-tmin  =  300
-tmax  = 3000
-tstep =  300
 ncpu = 7
 verb = 1
 """)

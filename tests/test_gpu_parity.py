@@ -1,0 +1,335 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle
+(oracle/lbl_oracle.c) and against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).
+
+Tolerances (BASELINE.json north_star): extinction within 1e-10 of each layer's peak in fp64,
+identical ethresh line selection (checked through the nskip/neval counters); Voigt table
+within 1e-12 relative; interp_ec bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from pyratbay_b200 import constants as pc
+
+pytestmark = pytest.mark.gpu
+
+TOL_PEAK = 1e-10     # relative to each layer's peak extinction
+TOL_VOIGT = 1e-12    # relative, per profile sample
+
+
+def _engine_for(case, profile="device"):
+    """Engine loaded with the static inputs of `case`; Voigt table built on the device
+    ('device') or adopted from the oracle's host table ('host')."""
+    from pyratbay_b200.engine import Engine
+    eng = Engine(0)
+    eng.set_grid(case.spec.wn, case.spec.own, case.spec.odivisors)
+    eng.set_species(case.atm.mol_radius, case.atm.mol_mass, case.iso_atm_index,
+                    case.iso_mass, case.iso_ratio)
+    eng.set_lines(case.lwn, case.elow, case.gf, case.isoid)
+    if profile == "device":
+        size = case.size_in.copy()
+        index = np.zeros_like(size)
+        eng.build_voigt(case.lorentz, case.doppler, case.spec.ownstep, size, index,
+                        case.cutoff)
+        assert np.array_equal(size, case.size)
+        assert np.array_equal(index, case.index)
+    else:
+        eng.set_voigt(case.lorentz, case.doppler, case.size, case.index, case.profile,
+                      case.cutoff)
+    return eng
+
+
+def _oracle_units(case, temps, dens, isoz, iso_iext, nextinct, add, resolution):
+    orc = helpers.oracle_module()
+    nrows = 1 if add else nextinct
+    out = np.zeros((len(temps), nrows, case.spec.nwave))
+    cnt = np.zeros((len(temps), 4), np.int64)
+    for u in range(len(temps)):
+        ext = np.zeros((nextinct, case.spec.nwave))
+        orc.extinction(ext, *case.unit_args(temps[u], dens[u], isoz[u], iso_iext),
+                       0, int(add), int(resolution), counters=cnt[u])
+        out[u] = ext[:nrows]
+    return out, cnt
+
+
+def _peak_err(got, want):
+    peak = np.max(np.abs(want), axis=-1, keepdims=True)
+    peak[peak == 0] = 1.0
+    return np.max(np.abs(got - want) / peak)
+
+
+# ---------------------------------------------------------------------------- Voigt grid
+def test_voigt_grid_matches_oracle_and_reference_golden():
+    from pyratbay_b200.engine import voigt_grid
+    case = helpers.mock_case()
+    g = helpers.golden("mock_voigt.npz")
+    size = case.size_in.copy()
+    index = np.zeros_like(size)
+    profile = np.zeros(case.voigt.profile_len)
+    assert voigt_grid(profile, size, index, case.lorentz, case.doppler,
+                      case.spec.ownstep) == 1
+    assert np.array_equal(size, g["size"])
+    assert np.array_equal(index, g["index"])
+    # against the oracle, every sample
+    ref = case.profile
+    nz = ref > 0
+    assert np.max(np.abs(profile[nz] / ref[nz] - 1.0)) < TOL_VOIGT
+    assert np.all(profile[~nz] == 0.0)
+    # against the reference's own table (strided golden samples, whole edge profiles)
+    stride = int(g["stride"])
+    want = g["profile_strided"]
+    got = profile[::stride]
+    nz = want > 0
+    assert np.max(np.abs(got[nz] / want[nz] - 1.0)) < TOL_VOIGT
+    for key, (m, n) in {"profile_first": (0, 0), "profile_mid": (40, 10),
+                        "profile_last": (-1, -1)}.items():
+        seg = profile[index[m, n]:index[m, n] + 2 * size[m, n] + 1]
+        assert np.max(np.abs(seg / g[key] - 1.0)) < TOL_VOIGT
+    assert abs(np.sum(profile) / float(g["profile_sum"]) - 1.0) < 1e-12
+
+
+def test_voigt_known_answer_of_reference_test_str():
+    """The 1.1-1.7 um H2O Voigt grid pinned by the reference's tests/test_str.py:338-366."""
+    from pyratbay_b200.spectrum import Spectrum
+    from pyratbay_b200.voigt import Voigt
+    from pyratbay_b200.engine import Engine
+    g = helpers.golden("voigt_h2o_1.1-1.7um.npz")
+    spec = Spectrum(wl_low=1.1 * pc.um, wl_high=1.7 * pc.um, wnstep=1.0, wnosamp=2160)
+    atm = helpers.mock_atmosphere()
+    eng = Engine(0)
+    iso_atm_index = np.full(4, list(atm.species).index("H2O"))
+    # no tmin/tmax: the Voigt width bounds default to 100-3000 K (pyrat/voigt.py:35-36)
+    v = Voigt(spec, atm, iso_atm_index, eng, extent=100.0, cutoff=25.0)
+    # numbers printed in test_str.py:352-365
+    assert list(v.size[0, [0, 1, -2, -1]]) == [1072, 1120, 8687, 9074]
+    assert list(v.size[-1, [0, -1]]) == [54000, 54000]
+    assert list(v.index[0, [0, 1, -2, -1]]) == [0, 2145, 341896, 359271]
+    assert list(v.index[1, [0, 1, -2, -1]]) == [377420, 379565, 719318, 736693]
+    assert v.index[-2, 0] == 46933096 and v.index[-1, -1] == 47041097
+    assert np.array_equal(v.size, g["size"]) and np.array_equal(v.index, g["index"])
+    prof = v.profile
+    assert len(prof) == int(g["profile_len"])
+    first = prof[v.index[0, 0]:v.index[0, 0] + 2 * v.size[0, 0] + 1]
+    last = prof[v.index[-1, -1]:v.index[-1, -1] + 2 * v.size[-1, -1] + 1]
+    assert ["%.5e" % x for x in first[[0, 1, -2, -1]]] == \
+        ["2.85914e-08", "2.86448e-08", "2.86448e-08", "2.85914e-08"]
+    assert ["%.5e" % x for x in last[[0, 1, -2, -1]]] == \
+        ["4.99389e-03", "4.99404e-03", "4.99404e-03", "4.99389e-03"]
+    want = g["profile_strided"]
+    got = prof[::int(g["stride"])]
+    nz = want > 0
+    assert np.max(np.abs(got[nz] / want[nz] - 1.0)) < TOL_VOIGT
+    assert np.all(got[~nz] == 0.0)
+    eng.close()
+
+
+# ------------------------------------------------------------------- reference golden tables
+@pytest.mark.parametrize("resolution,golden_file", [
+    (None, "mock_opacity_table.npz"), (15000.0, "mock_opacity_table_R.npz")])
+def test_compute_opacity_matches_reference_table(tmp_path, resolution, golden_file):
+    """configs[0]: pbay -c opacity on the mock HITRAN H2O TLI, through the Pyrat-shaped API."""
+    import pyratbay_b200 as pb
+    g = helpers.golden(golden_file)
+    inputs = dict(
+        runmode="opacity", tlifile=os.path.join(helpers.GOLDEN, "mock_hitran_h2o.tli"),
+        wl_low=1.00 * pc.um, wl_high=1.01 * pc.um, wnstep=1.0, wnosamp=2160,
+        resolution=resolution, voigt_extent=100.0, tmin=300.0, tmax=3000.0, tstep=300.0,
+        sampled_cs=[str(tmp_path / "table.npz")], verb=0)
+    pyrat = pb.Pyrat(inputs, atm=helpers.mock_atmosphere())
+    pyrat.compute_opacity()
+    units, species, temp, press, wn, table = pb.io.read_opacity(inputs["sampled_cs"][0])
+    assert species == "H2O" and units["pressure"] == "bar"
+    assert np.array_equal(temp, g["temp"]) and np.array_equal(wn, g["wn"])
+    assert np.array_equal(press, g["press"])
+    assert table.shape == g["etable"].shape
+    assert _peak_err(table, g["etable"]) < TOL_PEAK
+
+
+def test_forward_model_matches_reference():
+    """LBL branch of pyrat.run: co-added extinction for all layers, one-layer per-species
+    extinction and skip_mol (golden from the reference's Line_By_Line)."""
+    import pyratbay_b200 as pb
+    g = helpers.golden("mock_forward.npz")
+    inputs = dict(
+        tlifile=os.path.join(helpers.GOLDEN, "mock_hitran_h2o.tli"),
+        wl_low=1.00 * pc.um, wl_high=1.01 * pc.um, wnstep=1.0, wnosamp=2160,
+        voigt_extent=100.0, tmin=300.0, tmax=3000.0, tstep=300.0, verb=0)
+    pyrat = pb.Pyrat(inputs, atm=helpers.mock_atmosphere())
+    assert np.array_equal(pyrat.atm.d, g["d"])
+    ec = pyrat.calc_lbl_extinction()
+    assert _peak_err(ec, g["ec_all"]) < TOL_PEAK
+    ec31, label = pyrat.get_ec(31)
+    assert label == ["H2O"]
+    assert _peak_err(ec31, g["ec_layer31"]) < TOL_PEAK
+    skipped = pyrat.calc_lbl_extinction(skip_mol=["H2O"])
+    assert np.all(skipped == 0.0) and np.all(g["ec_skip"] == 0.0)
+
+
+# ------------------------------------------------------------------------ oracle, synthetic
+@pytest.mark.parametrize("kwargs", [
+    dict(),                                            # resample, defaults
+    dict(ethresh=1e-6),                                # many skipped lines
+    dict(cutoff=0.0, extent=20.0),                     # no fixed cutoff
+    dict(resolution=8000.0),                           # constant-R (2-point interpolation)
+    dict(nlines=200000, wnosamp=120),                  # dense: heavy co-adding
+    dict(wnstep=0.25, wnosamp=360, wnlow=9000.0, wnhigh=9060.0),
+])
+def test_extinction_matches_oracle_synthetic(kwargs):
+    case = helpers.synthetic_case(**kwargs)
+    eng = _engine_for(case, profile="host")
+    atm = case.atm
+    temps = atm.temp
+    dens = atm.d
+    isoz = helpers.partition(case, temps).T
+    resolution = case.spec.interpolate
+    for add in (0, 1):
+        want, wcnt = _oracle_units(case, temps, dens, isoz, case.iso_mol_index, 1, add,
+                                   resolution)
+        got, cnt = eng.extinction_batch(temps, dens, isoz, case.iso_mol_index, 1,
+                                        case.ethresh, add, resolution, counters=True)
+        assert got.shape == want.shape
+        assert np.array_equal(cnt[:, :4], wcnt), "nadd/nskip/neval/sample counters differ"
+        assert _peak_err(got, want) < TOL_PEAK
+    eng.close()
+
+
+def test_extinction_device_voigt_table_end_to_end():
+    """Same as above but with the Voigt table built on the device (both kernels chained)."""
+    case = helpers.synthetic_case(nlines=5000)
+    eng = _engine_for(case, profile="device")
+    temps, dens = case.atm.temp, case.atm.d
+    isoz = helpers.partition(case, temps).T
+    want, _ = _oracle_units(case, temps, dens, isoz, case.iso_mol_index, 1, 1, 0)
+    got = eng.extinction_batch(temps, dens, isoz, case.iso_mol_index, 1, case.ethresh, 1, 0)
+    assert _peak_err(got, want) < TOL_PEAK
+    eng.close()
+
+
+def test_multi_row_and_skipped_isotopes():
+    """add=0 with two output rows (isotopes mapped to different species rows) and one
+    isotope disabled through iso_iext=-1 (skip_mol, pyrat/extinction.py:165-168)."""
+    case = helpers.synthetic_case(nlines=8000)
+    eng = _engine_for(case, profile="host")
+    temps, dens = case.atm.temp[:4], case.atm.d[:4]
+    isoz = helpers.partition(case, temps).T
+    iext = np.array([0, 1, -1, 1])
+    want, wcnt = _oracle_units(case, temps, dens, isoz, iext, 2, 0, 0)
+    got, cnt = eng.extinction_batch(temps, dens, isoz, iext, 2, case.ethresh, 0, 0,
+                                    counters=True)
+    assert got.shape == (4, 2, case.spec.nwave)
+    assert np.array_equal(cnt[:, :4], wcnt)
+    assert _peak_err(got, want) < TOL_PEAK
+    eng.close()
+
+
+def test_partition_tables_on_engine_and_shared_temperature_passes():
+    """unit_isoz=NULL uses the engine's Z(T) tables; units sharing (T, Z) share one
+    strengths pass (table mode: many pressures per temperature)."""
+    case = helpers.synthetic_case(nlines=5000)
+    eng = _engine_for(case, profile="host")
+    eng.set_partition(case.db.temp, case.db.iso_pf)
+    temps = np.repeat([500.0, 1500.5, 2500.25], 3)
+    press = np.tile([1e-4, 1e-1, 10.0], 3)
+    dens = case.atm.vmr[0] * press[:, None] * pc.bar / (pc.k * temps[:, None])
+    isoz = helpers.partition(case, temps).T
+    want, _ = _oracle_units(case, temps, dens, isoz, case.iso_mol_index, 1, 0, 0)
+    got = eng.extinction_batch(temps, dens, None, case.iso_mol_index, 1, case.ethresh, 0, 0)
+    assert _peak_err(got, want) < TOL_PEAK
+    eng.close()
+
+
+def test_edge_cases_empty_and_out_of_window_lines():
+    case = helpers.synthetic_case(nlines=2000)
+    from pyratbay_b200.engine import Engine
+    eng = Engine(0)
+    eng.set_grid(case.spec.wn, case.spec.own, case.spec.odivisors)
+    eng.set_species(case.atm.mol_radius, case.atm.mol_mass, case.iso_atm_index,
+                    case.iso_mass, case.iso_ratio)
+    eng.set_voigt(case.lorentz, case.doppler, case.size, case.index, case.profile,
+                  case.cutoff)
+    temps, dens = case.atm.temp[:2], case.atm.d[:2]
+    isoz = helpers.partition(case, temps).T
+    # no lines at all
+    eng.set_lines(np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0, int))
+    out = eng.extinction_batch(temps, dens, isoz, case.iso_mol_index, 1, 1e-30, 1, 0)
+    assert out.shape == (2, 1, case.spec.nwave) and np.all(out == 0.0)
+    # every line outside the window
+    eng.set_lines(np.array([10.0, 20.0]), np.ones(2), np.ones(2), np.zeros(2, int))
+    assert eng.line_stats() == {"in_window": 0, "groups": 0, "nadd": 0}
+    out = eng.extinction_batch(temps, dens, isoz, case.iso_mol_index, 1, 1e-30, 1, 0)
+    assert np.all(out == 0.0)
+    # lines on the window edges and duplicates on one fine sample
+    own = case.spec.own
+    lw = np.array([own[0], own[5], own[5], own[5] + 0.4 * case.spec.ownstep, own[-1]])
+    eng.set_lines(lw, np.full(5, 100.0), np.full(5, 1e-6), np.zeros(5, int))
+    c2 = helpers.Case(**{**case.__dict__, "lwn": lw, "elow": np.full(5, 100.0),
+                         "gf": np.full(5, 1e-6), "isoid": np.zeros(5, int)})
+    want, wcnt = _oracle_units(c2, temps, dens, isoz, case.iso_mol_index, 1, 1, 0)
+    got, cnt = eng.extinction_batch(temps, dens, isoz, case.iso_mol_index, 1, 1e-30, 1, 0,
+                                    counters=True)
+    assert np.array_equal(cnt[:, :4], wcnt)
+    assert _peak_err(got, want) < TOL_PEAK
+    # zero units
+    out = eng.extinction_batch(np.zeros(0), np.zeros((0, case.atm.nmol)),
+                               np.zeros((0, 4)), case.iso_mol_index, 1, 1e-30, 1, 0)
+    assert out.shape == (0, 1, case.spec.nwave)
+    eng.close()
+
+
+def test_error_behaviour():
+    from pyratbay_b200.engine import Engine
+    from pyratbay_b200._lib import PB200Error
+    case = helpers.synthetic_case(nlines=2000)
+    eng = Engine(0)
+    with pytest.raises(PB200Error):   # lines before grid
+        eng.set_lines(case.lwn, case.elow, case.gf, case.isoid)
+    eng.set_grid(case.spec.wn, case.spec.own, case.spec.odivisors)
+    eng.set_species(case.atm.mol_radius, case.atm.mol_mass, case.iso_atm_index,
+                    case.iso_mass, case.iso_ratio)
+    with pytest.raises(PB200Error):   # unsorted within an isotope
+        eng.set_lines(case.lwn[::-1].copy(), case.elow, case.gf, case.isoid)
+    with pytest.raises(PB200Error):   # batch before voigt/lines
+        eng.extinction_batch(case.atm.temp, case.atm.d, None, case.iso_mol_index, 1, 1e-30,
+                             1, 0)
+    eng.close()
+
+
+# ----------------------------------------------------------------------- table interpolation
+def test_interp_ec_bit_exact_vs_oracle():
+    from pyratbay_b200.engine import interp_ec, interp_ec_per_mol
+    orc = helpers.oracle_module()
+    rng = np.random.default_rng(3)
+    nspec, ntemp, nlayers, nwave = 3, 7, 11, 1000
+    table = rng.uniform(1e-30, 1e-18, (nspec, ntemp, nlayers, nwave))
+    tgrid = np.linspace(300.0, 3000.0, ntemp)
+    temp = rng.uniform(300.0, 3000.0, nlayers)
+    temp[0], temp[1], temp[2] = 300.0, 3000.0, tgrid[3]   # grid nodes and ends
+    dens = rng.uniform(1e8, 1e18, (nlayers, nspec))
+    for fn_gpu, fn_cpu, shape in ((interp_ec, orc.interp_ec, (nlayers, nwave)),
+                                  (interp_ec_per_mol, orc.interp_ec_per_mol,
+                                   (nspec, nlayers, nwave))):
+        for lay1, lay2 in ((0, nlayers), (3, 4), (2, 50)):
+            a = rng.uniform(0.0, 1e-3, shape)
+            b = a.copy()
+            fn_gpu(a, table, tgrid, temp, dens, lay1, lay2)
+            fn_cpu(b, table, tgrid, temp, dens, lay1, lay2)
+            assert np.array_equal(a, b)
+
+
+def test_line_sample_matches_reference():
+    import pyratbay_b200 as pb
+    g = helpers.golden("mock_line_sample.npz")
+    ls = pb.Line_Sample(os.path.join(helpers.GOLDEN, "mock_opacity_file.npz"))
+    temp, dens = g["temperature"], g["density"]
+    np.testing.assert_allclose(ls.calc_cross_section(temp), g["cs"], rtol=1e-14)
+    np.testing.assert_allclose(ls.calc_cross_section(temp, per_mol=True), g["cs_per_mol"],
+                               rtol=1e-14)
+    np.testing.assert_allclose(ls.calc_extinction_coefficient(temp, dens), g["ec"],
+                               rtol=1e-14)
+    np.testing.assert_allclose(ls.calc_extinction_coefficient(temp, dens, layer=20),
+                               g["ec_layer"], rtol=1e-14)
+    with pytest.raises(ValueError):
+        ls.calc_cross_section(np.full(ls.nlayers, 5000.0))
