@@ -124,12 +124,23 @@ def read_tli_file(tli_file, wn_low, wn_high, log=None):
         n = int(n)
         block = wn_all[offset:offset + n]
         if n > 0:
-            # tools.binsearch semantics (tools/tools.py:219-311): first record >= wn_low and
-            # last record <= wn_high; a block entirely outside the window is skipped.
-            ifirst = int(np.searchsorted(block, wn_low, side='left'))
-            ilast = int(np.searchsorted(block, wn_high, side='right')) - 1
-            if ifirst < n and ilast >= 0 and ilast >= ifirst:
-                segments.append((offset + ifirst, ilast - ifirst + 1))
+            # tools.binsearch (tools/tools.py:219-311): index of the first record >= wn_low
+            # (-1 if the whole block lies below) and of the last record <= wn_high (-1 if
+            # the whole block lies above).
+            ifirst = -1 if block[-1] < wn_low else int(np.searchsorted(block, wn_low, 'left'))
+            ilast = -1 if wn_high < block[0] else int(np.searchsorted(block, wn_high, 'right')) - 1
+            # line_by_line.py:423-432 adds the block offset BEFORE testing the -1 sentinels,
+            # so for every block but the first a block lying entirely below the window is
+            # not skipped: the reader returns the previous block's last record again plus
+            # the whole block.  Kept bug-for-bug: the reference's tables contain that
+            # duplicated line, and parity is defined on its output.  (The out-of-window
+            # lines are dropped later by the window test of _extcoeff.c:215.)
+            ifirst += offset
+            ilast += offset
+            if ifirst >= 0 and ilast >= 0:
+                nread = ilast - ifirst + 1
+                if nread > 0:
+                    segments.append((ifirst, nread))
         offset += n
     nlt = sum(n for _, n in segments)
     wn = np.empty(nlt, np.double)
@@ -198,7 +209,7 @@ def write_tli(tli_file, databases, lines, wn_min, wn_max):
 # H2O isotopologues of the benchmark line lists (values as in the reference's
 # pyratbay/data/isotopes.dat:146-149 and tests/test_tli.py:32-35).
 H2O_ISOTOPES = {
-    'names': ['161', '181', '171', '162'],
+    'names': ['116', '118', '117', '126'],
     'mass': [18.010560, 20.014810, 19.014780, 19.016740],
     'ratio': [0.997317300, 0.001999827, 0.000371884, 0.000310693],
 }

@@ -1,0 +1,277 @@
+"""CPU tests of the host-side logic and of the C-ABI library's surface (no GPU needed)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+from pyratbay_b200 import constants as pc
+
+
+# ------------------------------------------------------------------------------- TLI files
+def test_read_tli_file_matches_reference_windows():
+    from pyratbay_b200.tli import read_tli_file
+    g = helpers.golden("tli_window_cases.npz")
+    tli = os.path.join(helpers.GOLDEN, "mock_hitran_h2o.tli")
+    k = 0
+    while f"w{k}_range" in g:
+        lo, hi = g[f"w{k}_range"]
+        dbs, wn, gf, elow, iso = read_tli_file(tli, lo, hi)
+        assert np.array_equal(wn, g[f"w{k}_wn"]), k
+        assert np.array_equal(gf, g[f"w{k}_gf"])
+        assert np.array_equal(elow, g[f"w{k}_elow"])
+        assert np.array_equal(iso, g[f"w{k}_iso"])
+        k += 1
+    assert k == 7
+    db = dbs[0]
+    # header facts printed by the reference's tests/test_tli.py:16-38
+    assert db.name == "HITRAN H2O" and db.molname == "H2O"
+    assert db.niso == 4 and db.ntemp == 1201
+    assert [str(x) for x in db.iso_name] == ["116", "118", "117", "126"]
+    np.testing.assert_allclose(db.iso_mass, [18.0106, 20.0148, 19.0148, 19.0167], atol=1e-4)
+    dbs, wn, gf, elow, iso = read_tli_file(tli, 0.0, 1e5)
+    assert len(wn) == 888
+    assert list(np.bincount(iso)) == [672, 148, 62, 6]
+    for i in range(4):
+        assert np.all(np.diff(wn[iso == i]) >= 0)
+
+
+def test_tli_write_read_round_trip_and_errors(tmp_path):
+    from pyratbay_b200 import tli as ptli
+    path = str(tmp_path / "syn.tli")
+    db = ptli.make_synthetic_tli(path, 5000, 4000.0, 4100.0, seed=3)
+    dbs, wn, gf, elow, iso = ptli.read_tli_file(path, 0.0, 1e6)
+    w2, e2, g2, i2, counts = ptli.synthetic_lines(5000, 4000.0, 4100.0, seed=3)
+    assert np.array_equal(wn, w2) and np.array_equal(elow, e2) and np.array_equal(gf, g2)
+    assert np.array_equal(iso, i2) and list(counts) == [3750, 750, 350, 150]
+    assert dbs[0].niso == 4 and np.array_equal(dbs[0].iso_pf, db.iso_pf)
+    # window extraction keeps per-isotope blocks
+    _, wn, _, _, iso = ptli.read_tli_file(path, 4040.0, 4050.0)
+    assert np.all((wn >= 4040.0) & (wn <= 4050.0)) and np.all(np.diff(iso) >= 0)
+    # empty window
+    _, wn, _, _, _ = ptli.read_tli_file(path, 10.0, 20.0)
+    assert len(wn) == 0
+    # truncated file
+    bad = str(tmp_path / "bad.tli")
+    open(bad, "wb").write(open(path, "rb").read()[:-7])
+    with pytest.raises(ValueError):
+        ptli.read_tli_file(bad, 0.0, 1e6)
+
+
+# ----------------------------------------------------------------------------- grids, sizing
+def test_spectrum_grids_match_reference():
+    from pyratbay_b200.spectrum import Spectrum, constant_resolution_spectrum
+    g = helpers.golden("mock_opacity_table.npz")
+    spec = Spectrum(wl_low=1.00 * pc.um, wl_high=1.01 * pc.um, wnstep=1.0, wnosamp=2160)
+    assert np.array_equal(spec.wn, g["wn"])
+    assert spec.own[0] == float(g["own0"]) and spec.ownstep == float(g["ownstep"])
+    assert spec.onwave == int(g["onwave"])
+    assert np.array_equal(spec.odivisors, g["odivisors"])
+    # default oversampling: first highly composite h with wnstep/h <= 4e-4 (spectrum.py:192-195)
+    assert Spectrum(wnlow=100.0, wnhigh=200.0, wnstep=1.0).wnosamp == 2520
+    gR = helpers.golden("mock_opacity_table_R.npz")
+    specR = Spectrum(wl_low=1.00 * pc.um, wl_high=1.01 * pc.um, wnstep=1.0, wnosamp=2160,
+                     resolution=15000.0)
+    assert np.array_equal(specR.wn, gR["wn"]) and specR.interpolate
+    # docstring example of spec_tools.py:483-492
+    wl = constant_resolution_spectrum(0.5, 4.0, 5.5)
+    np.testing.assert_allclose(wl[:4], [0.5, 0.6, 0.72, 0.864])
+    assert len(wl) == 12
+    with pytest.raises(ValueError):
+        Spectrum(wnlow=200.0, wnhigh=100.0, wnstep=1.0)
+    with pytest.raises(ValueError):
+        Spectrum(wnlow=100.0, wnhigh=200.0)
+
+
+def test_broadening_known_answers():
+    from pyratbay_b200 import broadening as b
+    # docstring examples of broadening.py:394-407 and :458-471 (tests/test_broadening.py:130-155)
+    dmin, lmin = b.min_widths(100.0, 3000.0, 1.0 / (10.0 * pc.um), 18.015, 1.6 * pc.A, 1e-5)
+    assert f"{dmin:.2e}" == "8.44e-04" and f"{lmin:.2e}" == "2.21e-07"
+    dmax, lmax = b.max_widths(100.0, 3000.0, 1.0 / (1.0 * pc.um), 18.015, 1.6 * pc.A, 100.0)
+    assert f"{dmax:.2e}" == "4.62e-02" and f"{lmax:.2e}" == "1.21e+01"
+
+
+def test_voigt_sizing_matches_reference():
+    g = helpers.golden("mock_voigt.npz")
+    case = helpers.mock_case(with_profile=False)
+    v = case.voigt
+    assert np.array_equal(v.lorentz, g["lorentz"]) and np.array_equal(v.doppler, g["doppler"])
+    assert v.profile_len == int(g["profile_len"])
+    # skipped profiles are 0 before the grid call and never in column 0
+    assert np.all(v.size[:, 0] > 0)
+    computed = v.size > 0
+    assert np.array_equal(v.size[computed], g["size"][computed])
+    from pyratbay_b200._lib import PB200Error
+    with pytest.raises(PB200Error):
+        v.profile     # no engine -> no table, never a CPU fallback
+
+
+def test_atmosphere_and_config(tmp_path):
+    from pyratbay_b200 import atmosphere as pa
+    from pyratbay_b200 import tools as pt
+    atm = helpers.mock_atmosphere()
+    a = helpers.golden("mock_atmosphere.npz")
+    assert np.array_equal(atm.mol_mass, a["mol_mass"])
+    assert np.array_equal(atm.mol_radius, a["mol_radius"])
+    assert np.array_equal(atm.d, a["d"])
+    # .atm round trip
+    atmfile = tmp_path / "uniform.atm"
+    with open(atmfile, "w") as f:
+        f.write("# test\n@PRESSURE\nbar\n@TEMPERATURE\nkelvin\n@ABUNDANCE\nvolume\n"
+                "@SPECIES\nH2  He  H2O\n\n@DATA\n")
+        for p, t in zip(atm.press[:5], atm.temp[:5]):
+            f.write(f"{p:.6e} {t:.3f} 8.5e-01 1.49e-01 4.0e-04\n")
+    species, press, temp, vmr = pa.read_atm(str(atmfile))
+    assert species == ["H2", "He", "H2O"] and vmr.shape == (5, 3)
+    np.testing.assert_allclose(press, atm.press[:5], rtol=1e-6)
+    cfg = tmp_path / "opacity.cfg"
+    cfg.write_text("[pyrat]\nrunmode = opacity\nlogfile = out/table.log\n"
+                   f"atmfile = {atmfile}\ntlifile = a.tli\nwl_low = 1.1 um\nwl_high = 1.7 um\n"
+                   "wnstep = 1.0\nwnosamp = 2160\nvoigt_extent = 100.0\ntmin = 300\n"
+                   "tmax = 3000\ntstep = 300\nncpu = 7\nverb = 2\n")
+    args = pt.parse(str(cfg))
+    assert args.runmode == "opacity" and args.wnosamp == 2160 and args.voigt_extent == 100.0
+    assert abs(args.wl_low - 1.1e-4) < 1e-18 and args.ethresh == 1e-30
+    assert args.voigt_cutoff == 25.0 and args.voigt_ndop == 50 and args.voigt_nlor == 100
+    assert args.sampled_cs[0].endswith("out/table.npz")      # parser.py:695-696
+    assert os.path.isabs(args.tlifile[0])
+    with pytest.raises(ValueError):
+        pt.parse(str(tmp_path / "missing.cfg"))
+
+
+def test_opacity_file_round_trip(tmp_path):
+    from pyratbay_b200 import io
+    rng = np.random.default_rng(0)
+    temp, press = np.linspace(300, 3000, 4), np.logspace(-6, 2, 5)
+    wn = np.linspace(1000, 1010, 11)
+    table = rng.uniform(size=(4, 5, 11))
+    path = str(tmp_path / "t.npz")
+    io.write_opacity(path, "H2O", temp, press, wn, table)
+    with np.load(path, allow_pickle=True) as f:     # layout of io.py:594-606
+        assert sorted(f.files) == ["opacity", "pressure", "species", "temperature", "units",
+                                   "wavenumber"]
+        assert list(f["species"]) == ["H2O"]
+        assert f["units"].item()["pressure"] == "bar"
+    units, species, t2, p2, w2, tab2 = io.read_opacity(path)
+    assert species == "H2O" and np.array_equal(tab2, table) and np.array_equal(p2, press)
+    assert io.read_opacity(path, extract="opacity").shape == (4, 5, 11)
+    assert io.read_opacity(path, extract="arrays")[0] == "H2O"
+    with pytest.raises(ValueError):
+        io.write_opacity(path, ["H2O"], temp, press, wn, table)
+    # the reference's own file reads back identically
+    _, sp, t, p, w, tab = io.read_opacity(os.path.join(helpers.GOLDEN, "mock_opacity_file.npz"))
+    g = helpers.golden("mock_opacity_table.npz")
+    assert sp == "H2O" and np.array_equal(tab, g["etable"]) and np.array_equal(w, g["wn"])
+
+
+def test_interpolate_opacity_regridding(tmp_path):
+    from pyratbay_b200.line_sampling import interpolate_opacity
+    path = os.path.join(helpers.GOLDEN, "mock_opacity_file.npz")
+    g = helpers.golden("mock_opacity_table.npz")
+    same = interpolate_opacity(path, g["temp"], g["press"])
+    assert np.array_equal(same, g["etable"])
+    temp2 = np.array([450.0, 1234.0])
+    press2 = np.array([1e-7, 3e-3, 50.0])
+    cs = interpolate_opacity(path, temp2, press2)
+    assert cs.shape == (2, 3, 100) and np.all(np.isfinite(cs)) and np.all(cs >= 0)
+    # log-linear between bracketing nodes
+    lo, hi = g["etable"][0], g["etable"][1]
+    with np.errstate(divide="ignore"):
+        want = np.exp(0.5 * (np.maximum(np.log(lo), -230) + np.maximum(np.log(hi), -230)))
+    cs_t = interpolate_opacity(path, np.array([450.0, 3000.0]), None)
+    np.testing.assert_allclose(cs_t[0], want, rtol=1e-12)
+
+
+# --------------------------------------------------------------------------- C-ABI surface
+def test_c_abi_library_exports_every_declared_symbol():
+    from pyratbay_b200 import _lib, build
+    build.build_library()
+    header = open(os.path.join(helpers.ROOT, "include", "pb200_lbl.h")).read()
+    declared = sorted(set(re.findall(r"\b(pb200_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 22
+    assert sorted(_lib.EXPORTS) == declared
+    lib = ctypes.CDLL(_lib.lib_path())
+    for name in declared:
+        assert hasattr(lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path()],
+                         capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(rf"\bT {name}\b", out), name
+    assert b"sm_100a" in _lib.load().pb200_version()
+
+
+def test_product_path_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from pyratbay_b200 import _lib
+    from pyratbay_b200.engine import Engine, voigt_grid, interp_ec
+    assert _lib.device_count() == 0
+    with pytest.raises(_lib.PB200Error):
+        Engine(0)
+    with pytest.raises(_lib.PB200Error):
+        voigt_grid(np.zeros(10), np.ones((1, 1), np.int64), np.zeros((1, 1), np.int64),
+                   [1e-3], [1e-2], 1e-3)
+    with pytest.raises(_lib.PB200Error):
+        interp_ec(np.zeros((2, 3)), np.zeros((1, 2, 2, 3)), [1.0, 2.0], [1.5, 1.5],
+                  np.ones((2, 1)), 0, 2)
+    # raw ABI: status code and message
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.pb200_engine_create(ctypes.c_int(0), ctypes.byref(h)) == -2  # PB200_ENODEVICE
+    assert b"no CPU fallback" in lib.pb200_last_error()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(helpers.ROOT, "pyratbay_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(root, f)).read()
+                assert "import oracle" not in text and "lbl_oracle" not in text, f
+                assert "/root/reference" not in text, f
+
+
+# ------------------------------------------------------------------------- multi-GPU logic
+def test_partition_units():
+    from pyratbay_b200.parallel import partition_units
+    n = 1020
+    for world in (1, 2, 3, 8):
+        parts = [partition_units(n, r, world) for r in range(world)]
+        assert sorted(np.concatenate(parts)) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    cost = np.tile(np.logspace(0, 1.5, 51), 20)
+    parts = [partition_units(n, r, 8, cost) for r in range(8)]
+    assert sorted(np.concatenate(parts)) == list(range(n))
+    loads = [cost[p].sum() for p in parts]
+    assert max(loads) / min(loads) < 1.02
+
+
+def _gloo_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    sys.path.insert(0, helpers.ROOT)
+    from pyratbay_b200 import parallel
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
+                            world_size=world)
+    n_units, nwave = 23, 17
+    full = np.arange(n_units * nwave, dtype=np.double).reshape(n_units, nwave) ** 1.5
+    mine = parallel.partition_units(n_units, rank, world)
+    table = np.zeros((n_units, nwave))
+    table[mine] = full[mine]          # "compute" only this rank's units
+    parallel.assemble_rows(table, mine)
+    np.save(os.path.join(tmp, f"table_{rank}.npy"), table)
+    dist.destroy_process_group()
+
+
+def test_table_assembly_across_two_ranks_gloo(tmp_path):
+    import torch.multiprocessing as tmp_mp
+    port = 29500 + os.getpid() % 2000
+    tmp_mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    full = np.arange(23 * 17, dtype=np.double).reshape(23, 17) ** 1.5
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / f"table_{r}.npy"), full)
