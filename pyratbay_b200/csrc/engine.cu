@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -115,6 +116,11 @@ struct pb200_engine {
     DevBuf<double> d_profile, d_doppler;
     DevBuf<int> d_psize;
     DevBuf<long long> d_pindex;
+    // output-stride copy of the table (built on first use for constant-step output grids)
+    int tstride = 0;
+    DevBuf<double> d_tprofile;
+    DevBuf<long long> d_tbase;
+    DevBuf<int> d_trow;
 
     // species
     bool has_species = false;
@@ -159,6 +165,10 @@ struct pb200_engine {
         V.doppler = d_doppler.p;
         V.nlor = nlor;
         V.ndop = ndop;
+        V.tprofile = d_tprofile.p;
+        V.tbase = d_tbase.p;
+        V.trow = d_trow.p;
+        V.tstride = tstride;
         V.l_wn = d_lwn.p;
         V.l_elow = d_lelow.p;
         V.l_gf = d_lgf.p;
@@ -275,6 +285,8 @@ static int adopt_voigt_tables(pb200_engine *e, int nlor, int ndop, const double 
     e->nlor = nlor;
     e->ndop = ndop;
     e->cutoff = cutoff;
+    e->tstride = 0;  // the output-stride copy is rebuilt on demand
+    e->d_tprofile.release();
     e->lorentz.assign(lorentz, lorentz + nlor);
     e->doppler.assign(doppler, doppler + ndop);
     e->psize.resize((size_t)nlor * ndop);
@@ -525,6 +537,46 @@ int pb200_engine_line_stats(const pb200_engine *e, int64_t stats[3]) {
     return 0;
 }
 
+// Build (once per Voigt table and stride) the output-stride copy used by the coalesced
+// accumulate mode: every distinct profile becomes a [stride, Q] block.
+static int ensure_transposed(pb200_engine *e, int stride) {
+    if (e->tstride == stride && e->d_tprofile.p) return 0;
+    const size_t nslot = (size_t)e->nlor * e->ndop;
+    std::vector<long long> tbase(nslot), src, dst;
+    std::vector<int> trow(nslot), nbin, rowlen;
+    std::map<long long, size_t> seen;  // reference-layout start -> block id
+    long long total = 0;
+    for (size_t at = 0; at < nslot; at++) {
+        auto it = seen.find(e->pindex[at]);
+        if (it == seen.end()) {
+            const int nb = 2 * e->psize[at] + 1;
+            const int q = (nb + stride - 1) / stride;
+            seen.emplace(e->pindex[at], src.size());
+            src.push_back(e->pindex[at]);
+            dst.push_back(total);
+            nbin.push_back(nb);
+            rowlen.push_back(q);
+            tbase[at] = total;
+            trow[at] = q;
+            total += (long long)stride * q;
+        } else {
+            tbase[at] = dst[it->second];
+            trow[at] = rowlen[it->second];
+        }
+    }
+    e->tstride = 0;
+    int rc = e->d_tprofile.alloc((size_t)total);
+    if (!rc) rc = e->d_tbase.upload(tbase.data(), nslot, e->stream);
+    if (!rc) rc = e->d_trow.upload(trow.data(), nslot, e->stream);
+    if (rc) return rc;
+    rc = launch_transpose(e->stream, (int)src.size(), src.data(), dst.data(), nbin.data(),
+                          rowlen.data(), total, stride, e->d_profile.p, e->d_tprofile.p);
+    if (rc) return rc;
+    e->launches++;
+    e->tstride = stride;
+    return 0;
+}
+
 // ----------------------------------------------------------------------------------------
 static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
                      const double *unit_density, const double *unit_isoz,
@@ -651,6 +703,27 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
     }
     const int ntp = (int)tp_temp.size();
 
+    // Accumulate mode per unit: constant-step outputs read the output-stride table when the
+    // unit's dynamic stride ofactor*scale equals the table's stride (always true when
+    // wnstep/ownstep is the integer wnosamp); anything else uses the generic strided gather.
+    std::vector<int> unit_mode(n_units, resolution ? kModeLinterp : kModeStrided);
+    // PB200_ACC_MODE=strided forces the generic gather (used by the tests to cover it).
+    const char *force = std::getenv("PB200_ACC_MODE");
+    const bool allow_transposed = !(force && std::strcmp(force, "strided") == 0);
+    if (!resolution && allow_transposed) {
+        const int stride = (int)std::llround(wnstep / ownstep);
+        bool any = false;
+        for (int u = 0; u < n_units; u++)
+            if (stride >= 1 && (long long)units[u].ofactor * units[u].scale == stride) {
+                unit_mode[u] = kModeTransposed;
+                any = true;
+            }
+        if (any) {
+            int rc_t = ensure_transposed(e, stride);
+            if (rc_t) return rc_t;
+        }
+    }
+
     // Output buffer first, then chunk the strengths passes so that ksum[ntp_chunk, ngroups]
     // fits in 60% of what is left.
     int rc = 0;
@@ -700,13 +773,20 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         const int ntc = std::min(tp_chunk, ntp - tp0);
         std::vector<UnitParams> cu;
         std::vector<IsoUnit> ci;
-        while (pos < order.size() && unit_tp[order[pos]] < tp0 + ntc) {
-            const int u = order[pos++];
-            UnitParams U = units[u];
-            U.tpass = unit_tp[u] - tp0;
-            cu.push_back(U);
-            ci.insert(ci.end(), iso_units.begin() + (size_t)u * niso,
-                      iso_units.begin() + (size_t)(u + 1) * niso);
+        std::vector<int> cmode;
+        {
+            std::vector<int> members;
+            while (pos < order.size() && unit_tp[order[pos]] < tp0 + ntc) members.push_back(order[pos++]);
+            std::stable_sort(members.begin(), members.end(),
+                             [&](int a, int b) { return unit_mode[a] < unit_mode[b]; });
+            for (int u : members) {
+                UnitParams U = units[u];
+                U.tpass = unit_tp[u] - tp0;
+                cu.push_back(U);
+                cmode.push_back(unit_mode[u]);
+                ci.insert(ci.end(), iso_units.begin() + (size_t)u * niso,
+                          iso_units.begin() + (size_t)(u + 1) * niso);
+            }
         }
         PB_CUDA(cudaMemcpyAsync(e->d_tp_temp.p, tp_temp.data() + tp0, sizeof(double) * ntc,
                                 cudaMemcpyHostToDevice, st));
@@ -723,12 +803,14 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         if (rc) return rc;
         if (V.ngroups > 0) e->launches++;
         PB_CUDA(cudaEventRecord(e->ev[2], st));
-        // grid.y is limited to 65535 units per launch
-        for (size_t u0 = 0; u0 < cu.size(); u0 += 65535) {
-            const int nu = (int)std::min<size_t>(65535, cu.size() - u0);
+        // one launch per run of equal mode; grid.y is limited to 65535 units per launch
+        for (size_t u0 = 0; u0 < cu.size();) {
+            size_t u1 = u0;
+            while (u1 < cu.size() && cmode[u1] == cmode[u0] && u1 - u0 < 65535) u1++;
+            const int nu = (int)(u1 - u0);
             rc = launch_accumulate(st, V, nu, e->d_units.p + u0, e->d_iso_units.p + u0 * niso,
                                    e->d_iso_row.p, e->d_ksum.p, e->d_kmax.p, nrows, ethresh,
-                                   cutoff, resolution ? 1 : 0, d_out);
+                                   cutoff, cmode[u0], d_out);
             if (rc) return rc;
             e->launches++;
             if (counters) {
@@ -738,6 +820,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
                 if (rc) return rc;
                 if (V.ngroups > 0) e->launches++;
             }
+            u0 = u1;
         }
         PB_CUDA(cudaEventRecord(e->ev[3], st));
         // the host vectors cu/ci must stay alive until their copies have completed

@@ -22,6 +22,13 @@ struct StaticView {
     const long long *pindex;   // [nlor*ndop] start index
     const double *doppler;     // [ndop]
     int nlor, ndop;
+    // Output-stride ("transposed") copy of the Voigt table for constant-step output grids:
+    // profile p is stored as rows of every tstride-th sample, T[r][q] = profile[q*tstride+r],
+    // so the samples one line contributes to consecutive output points are contiguous.
+    const double *tprofile;
+    const long long *tbase;    // [nlor*ndop] start of the profile's transposed block
+    const int *trow;           // [nlor*ndop] row length Q = ceil((2*size+1)/tstride)
+    int tstride;               // fine samples per output sample (0: no transposed copy)
     // co-add groups (sorted by isotope, then wavenumber)
     const double *l_wn, *l_elow, *l_gf;   // in-window lines, member order
     const double *g_wn;                   // head-line wavenumber

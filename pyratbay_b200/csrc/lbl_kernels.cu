@@ -14,17 +14,34 @@
 // shared memory and then broadcast to the warp.
 #include "lbl_kernels.cuh"
 
+#include <algorithm>
 #include <climits>
+#include <vector>
 
 namespace pb200 {
 
+// Accumulation modes of kernel 3.
+//   kStrided    : constant-step output, samples gathered from the reference-layout table with
+//                 stride ofactor*scale (generic; any scale)
+//   kLinterp    : arbitrary output grid, two dynamic samples per output point (utils.h:139-163)
+//   kTransposed : constant-step output, samples gathered from the output-stride copy of the
+//                 table: consecutive output points read consecutive addresses (coalesced)
+enum AccMode { kStrided = 0, kLinterp = 1, kTransposed = 2 };
+
 struct Prep {
     double k;
-    long long base;  // profile index of dynamic sample j is base + ofactor*j
-    int jlo, jhi;    // dynamic-sample range [jlo, jhi)
+    long long base;  // sample for coordinate x is table[base + mult*x]
+    int lo, hi;      // coordinate range [lo, hi): dynamic index j, or output index m (kTransposed)
 };
 
+__device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
+    int q = a / b;
+    return (a % b < 0) ? q - 1 : q;
+}
+__device__ __forceinline__ int ceil_div_nonneg(int a, int b) { return (a + b - 1) / b; }
+
 // The per-group part of _extcoeff.c:264-299, identical integer/floating-point decisions.
+template <int MODE>
 __device__ __forceinline__ bool prepare_group(const StaticView &V, const UnitParams &U,
                                               const IsoUnit &I, const double *s_doppler,
                                               double kthr, double cutoff, double w, int iown,
@@ -47,9 +64,23 @@ __device__ __forceinline__ bool prepare_group(const StaticView &V, const UnitPar
         if (hi_cut < jhi) jhi = hi_cut;
     }
     out->k = k;
-    out->base = V.pindex[at] + (long long)half - (long long)iown;           // :283,303
-    out->jlo = jlo;
-    out->jhi = jhi;
+    if (MODE == kTransposed) {
+        // outputs m with scale*m in [jlo, jhi), m < mcount            (utils.h:130-133)
+        int mlo = ceil_div_nonneg(jlo, U.scale);
+        int mhi = jhi > 0 ? ceil_div_nonneg(jhi, U.scale) : 0;
+        if (mhi > U.mcount) mhi = U.mcount;
+        // profile sample of output m: half - iown + tstride*m = q*tstride + r
+        const int d = half - iown;
+        const int q0 = floor_div(d, V.tstride);
+        const int r = d - q0 * V.tstride;
+        out->base = V.tbase[at] + (long long)r * V.trow[at] + q0;
+        out->lo = mlo;
+        out->hi = mhi;
+    } else {
+        out->base = V.pindex[at] + (long long)half - (long long)iown;       // :283,303
+        out->lo = jlo;
+        out->hi = jhi;
+    }
     return true;
 }
 
@@ -104,7 +135,7 @@ strengths_kernel(StaticView V, const double *__restrict__ tp_temp,
 
 // ---------------------------------------------------------------------------------------
 // Kernel 3: output-owned accumulation.  grid = (tiles, units, rows), 256 threads.
-template <bool LINTERP>
+template <int MODE>
 __global__ void __launch_bounds__(256)
 accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
                   const IsoUnit *__restrict__ iso_units, const int *__restrict__ iso_row,
@@ -114,7 +145,7 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
     extern __shared__ double s_doppler[];  // [ndop]
     __shared__ double s_k[8][32];
     __shared__ long long s_base[8][32];
-    __shared__ int2 s_j[8][32];
+    __shared__ int2 s_r[8][32];
 
     for (int i = threadIdx.x; i < V.ndop; i += blockDim.x) s_doppler[i] = V.doppler[i];
     __syncthreads();
@@ -124,32 +155,36 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
     const int row = blockIdx.z;
     const int m = blockIdx.x * kTileOutputs + threadIdx.x;
     const bool in_grid = m < V.nwave;
+    const double *__restrict__ table = (MODE == kTransposed) ? V.tprofile : V.profile;
+    const int mult = (MODE == kTransposed) ? 1 : U.ofactor;            // address stride per x
+    const int fstride = (MODE == kTransposed) ? V.tstride : U.ofactor; // fine samples per x
 
-    // Dynamic samples this output needs: one (resample, utils.h:132) or two (linterp, :153-160).
-    int j0 = -1, j1 = -1;
+    // Coordinates this output needs: its own index (kTransposed), the dynamic sample
+    // scale*m (kStrided, utils.h:132) or the bracketing pair ilo, ilo+1 (kLinterp, :153-160).
+    int x0 = -1, x1 = -1;
     double wn_i = 0.0;
-    if (LINTERP) {
+    if (MODE == kLinterp) {
         if (in_grid) {
             wn_i = V.wn[m];
-            j0 = (int)ddiv(dsub(wn_i, V.wn0), U.dwnstep);
-            j1 = j0 + 1;
+            x0 = (int)ddiv(dsub(wn_i, V.wn0), U.dwnstep);
+            x1 = x0 + 1;
         }
     } else if (in_grid && m < U.mcount) {
-        j0 = U.scale * m;
+        x0 = (MODE == kTransposed) ? m : U.scale * m;
     }
-    int jmin = (j0 >= 0) ? j0 : INT_MAX;
-    int jmax = (j0 >= 0) ? (LINTERP ? j1 : j0) : INT_MIN;
-    jmin = __reduce_min_sync(0xffffffffu, jmin);
-    jmax = __reduce_max_sync(0xffffffffu, jmax);
+    int xmin = (x0 >= 0) ? x0 : INT_MAX;
+    int xmax = (x0 >= 0) ? (MODE == kLinterp ? x1 : x0) : INT_MIN;
+    xmin = __reduce_min_sync(0xffffffffu, xmin);
+    xmax = __reduce_max_sync(0xffffffffu, xmax);
 
     double acc0 = 0.0, acc1 = 0.0;
-    if (jmax >= jmin) {
+    if (xmax >= xmin) {
         const double *__restrict__ ks = ksum + (size_t)U.tpass * V.ngroups;
         for (int iso = 0; iso < V.niso; iso++) {
             if (iso_row[iso] != row) continue;
             const IsoUnit I = iso_units[(size_t)blockIdx.y * V.niso + iso];
-            long long flo = (long long)jmin * U.ofactor - I.reach;
-            long long fhi = (long long)jmax * U.ofactor + I.reach;
+            long long flo = (long long)xmin * fstride - I.reach;
+            long long fhi = (long long)xmax * fstride + I.reach;
             if (fhi < 0 || flo > V.onwn - 1) continue;
             if (flo < 0) flo = 0;
             if (fhi > V.onwn - 1) fhi = V.onwn - 1;
@@ -161,24 +196,24 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
             for (int c = glo; c < ghi; c += 32) {
                 const int g = c + lane;
                 Prep p;
-                p.k = 0.0; p.base = 0; p.jlo = 0; p.jhi = 0;
+                p.k = 0.0; p.base = 0; p.lo = 0; p.hi = 0;
                 if (g < ghi)
-                    prepare_group(V, U, I, s_doppler, kthr, cutoff, V.g_wn[g], V.g_iown[g],
-                                  ks[g], &p);
+                    prepare_group<MODE>(V, U, I, s_doppler, kthr, cutoff, V.g_wn[g], V.g_iown[g],
+                                        ks[g], &p);
                 s_k[warp][lane] = p.k;
                 s_base[warp][lane] = p.base;
-                s_j[warp][lane] = make_int2(p.jlo, p.jhi);
+                s_r[warp][lane] = make_int2(p.lo, p.hi);
                 __syncwarp();
                 const int n = min(32, ghi - c);
                 for (int t = 0; t < n; t++) {
-                    const int2 jr = s_j[warp][t];
-                    if (jr.y <= jmin || jr.x > jmax) continue;  // warp-uniform
+                    const int2 r = s_r[warp][t];
+                    if (r.y <= xmin || r.x > xmax) continue;  // warp-uniform
                     const double k = s_k[warp][t];
                     const long long base = s_base[warp][t];
-                    if (j0 >= jr.x && j0 < jr.y)
-                        acc0 = fma(k, __ldg(V.profile + base + (long long)U.ofactor * j0), acc0);
-                    if (LINTERP && j1 >= jr.x && j1 < jr.y)
-                        acc1 = fma(k, __ldg(V.profile + base + (long long)U.ofactor * j1), acc1);
+                    if (x0 >= r.x && x0 < r.y)
+                        acc0 = fma(k, __ldg(table + base + (long long)mult * x0), acc0);
+                    if (MODE == kLinterp && x1 >= r.x && x1 < r.y)
+                        acc1 = fma(k, __ldg(table + base + (long long)mult * x1), acc1);
                 }
                 __syncwarp();
             }
@@ -186,12 +221,39 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
     }
     if (in_grid) {
         double *dst = out + ((size_t)U.out_index * nrows + row) * (size_t)V.nwave;
-        if (LINTERP) {
-            const double wlo = dadd(V.wn0, dmul(U.dwnstep, (double)j0));
+        if (MODE == kLinterp) {
+            const double wlo = dadd(V.wn0, dmul(U.dwnstep, (double)x0));
             dst[m] = (acc0 * (wlo + U.dwnstep - wn_i) + acc1 * (wn_i - wlo)) / U.dwnstep;
         } else {
             dst[m] = acc0;  // 0 beyond mcount
         }
+    }
+}
+
+// One-time re-layout of the Voigt table: block of profile p is T[r][q] = P[q*stride + r].
+struct TransposeDesc {
+    long long src;    // start of the profile in the reference-layout table
+    long long dst;    // start of its transposed block
+    int nbin;         // 2*half+1
+    int rowlen;       // Q
+};
+
+__global__ void __launch_bounds__(256)
+transpose_kernel(const TransposeDesc *__restrict__ desc, int nprof, long long total, int stride,
+                 const double *__restrict__ profile, double *__restrict__ tprofile) {
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += step) {
+        int lo = 0, hi = nprof;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (desc[mid].dst <= gid) lo = mid; else hi = mid;
+        }
+        const TransposeDesc d = desc[lo];
+        const long long local = gid - d.dst;
+        const int r = (int)(local / d.rowlen), q = (int)(local % d.rowlen);
+        const long long s = (long long)q * stride + r;
+        tprofile[gid] = (s < d.nbin) ? profile[d.src + s] : 0.0;
     }
 }
 
@@ -217,23 +279,24 @@ counters_kernel(StaticView V, const UnitParams *__restrict__ units,
             const double kthr =
                 dmul(ethresh, __longlong_as_double((long long)kmax[(size_t)U.tpass * nrows + row]));
             Prep p;
-            if (prepare_group(V, U, I, s_doppler, kthr, cutoff, V.g_wn[g], V.g_iown[g],
-                              ksum[(size_t)U.tpass * V.ngroups + g], &p)) {
+            if (prepare_group<kStrided>(V, U, I, s_doppler, kthr, cutoff, V.g_wn[g],
+                                        V.g_iown[g], ksum[(size_t)U.tpass * V.ngroups + g],
+                                        &p)) {
                 eval = 1;
-                if (p.jhi > p.jlo) {
-                    dyn = (unsigned long long)(p.jhi - p.jlo);
+                if (p.hi > p.lo) {
+                    dyn = (unsigned long long)(p.hi - p.lo);
                     if (!linterp) {
                         // outputs m < mcount with scale*m in [jlo, jhi)
-                        long long mlo = ((long long)p.jlo + U.scale - 1) / U.scale;
-                        long long mhi = ((long long)p.jhi + U.scale - 1) / U.scale;
+                        long long mlo = ((long long)p.lo + U.scale - 1) / U.scale;
+                        long long mhi = ((long long)p.hi + U.scale - 1) / U.scale;
                         if (mhi > U.mcount) mhi = U.mcount;
                         if (mhi > V.nwave) mhi = V.nwave;
                         if (mhi > mlo) used = (unsigned long long)(mhi - mlo);
                     } else {
                         // outputs whose bracketing pair (ilo, ilo+1) touches [jlo, jhi): counted
                         // on the output grid by bisection; each touching output gathers <= 2.
-                        const double a = dadd(V.wn0, dmul(U.dwnstep, (double)(p.jlo - 1)));
-                        const double b = dadd(V.wn0, dmul(U.dwnstep, (double)p.jhi));
+                        const double a = dadd(V.wn0, dmul(U.dwnstep, (double)(p.lo - 1)));
+                        const double b = dadd(V.wn0, dmul(U.dwnstep, (double)p.hi));
                         int lo = 0, hi = V.nwave;
                         while (lo < hi) { int mid = (lo + hi) >> 1; if (V.wn[mid] < a) lo = mid + 1; else hi = mid; }
                         const int first = lo;
@@ -306,18 +369,41 @@ int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double
 int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
                       const UnitParams *units, const IsoUnit *iso_units, const int *iso_row,
                       const double *ksum, const unsigned long long *kmax, int nrows,
-                      double ethresh, double cutoff, int linterp, double *out) {
+                      double ethresh, double cutoff, int mode, double *out) {
     if (nunits == 0 || V.nwave == 0) return 0;
     dim3 grid((unsigned)((V.nwave + kTileOutputs - 1) / kTileOutputs), (unsigned)nunits,
               (unsigned)nrows);
     const size_t smem = sizeof(double) * V.ndop;
-    if (linterp)
-        accumulate_kernel<true><<<grid, 256, smem, st>>>(V, units, iso_units, iso_row, ksum,
-                                                         kmax, nrows, ethresh, cutoff, out);
+    if (mode == kLinterp)
+        accumulate_kernel<kLinterp><<<grid, 256, smem, st>>>(
+            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out);
+    else if (mode == kTransposed)
+        accumulate_kernel<kTransposed><<<grid, 256, smem, st>>>(
+            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out);
     else
-        accumulate_kernel<false><<<grid, 256, smem, st>>>(V, units, iso_units, iso_row, ksum,
-                                                          kmax, nrows, ethresh, cutoff, out);
+        accumulate_kernel<kStrided><<<grid, 256, smem, st>>>(
+            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out);
     PB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_transpose(cudaStream_t st, int nprof, const long long *src, const long long *dst,
+                     const int *nbin, const int *rowlen, long long total, int stride,
+                     const double *profile, double *tprofile) {
+    if (nprof == 0 || total == 0) return 0;
+    std::vector<TransposeDesc> desc(nprof);
+    for (int p = 0; p < nprof; p++) desc[p] = TransposeDesc{src[p], dst[p], nbin[p], rowlen[p]};
+    TransposeDesc *d_desc = nullptr;
+    PB_CUDA(cudaMalloc((void **)&d_desc, sizeof(TransposeDesc) * nprof));
+    PB_CUDA(cudaMemcpyAsync(d_desc, desc.data(), sizeof(TransposeDesc) * nprof,
+                            cudaMemcpyHostToDevice, st));
+    const long long want = (total + 255) / 256;
+    const int blocks = (int)std::min<long long>(want, 148LL * 32);
+    transpose_kernel<<<blocks, 256, 0, st>>>(d_desc, nprof, total, stride, profile, tprofile);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    cudaFree(d_desc);
+    if (err != cudaSuccess) return cuda_fail(err, "transpose_kernel", __FILE__, __LINE__);
     return 0;
 }
 

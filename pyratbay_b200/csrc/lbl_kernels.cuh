@@ -11,7 +11,15 @@ int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double
 int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
                       const UnitParams *units, const IsoUnit *iso_units, const int *iso_row,
                       const double *ksum, const unsigned long long *kmax, int nrows,
-                      double ethresh, double cutoff, int linterp, double *out);
+                      double ethresh, double cutoff, int mode, double *out);
+
+// mode values of launch_accumulate
+constexpr int kModeStrided = 0, kModeLinterp = 1, kModeTransposed = 2;
+
+// Build the output-stride copy of the Voigt table (one-time; synchronises `st`).
+int launch_transpose(cudaStream_t st, int nprof, const long long *src, const long long *dst,
+                     const int *nbin, const int *rowlen, long long total, int stride,
+                     const double *profile, double *tprofile);
 
 int launch_counters(cudaStream_t st, const StaticView &V, int nunits, const UnitParams *units,
                     const IsoUnit *iso_units, const int *iso_row, const double *ksum,
