@@ -55,4 +55,19 @@ __device__ __forceinline__ int nearest_index(const double *grid, int n, double v
     return (fabs(dsub(grid[hi], v)) < fabs(dsub(grid[lo], v))) ? hi : lo;
 }
 
+// Same result as nearest_index for a (roughly) log-spaced grid, in O(1): the bracket is
+// guessed from the IEEE exponent/mantissa bits (piecewise-linear log2, error < 0.09) and then
+// corrected exactly, so the returned index is identical for ANY increasing grid.
+//   hi0      = high 32 bits of grid[0]
+//   inv_step = (n-1) / log2(grid[n-1]/grid[0]) / 2^20
+__device__ __forceinline__ int nearest_index_log(const double *grid, int n, double v, int hi0,
+                                                 float inv_step) {
+    int lo = (int)((float)(__double2hiint(v) - hi0) * inv_step);
+    lo = max(0, min(lo, n - 2));
+    while (lo < n - 2 && grid[lo + 1] < v) lo++;
+    while (lo > 0 && !(grid[lo] < v)) lo--;
+    const int hi = lo + 1;
+    return (fabs(dsub(grid[hi], v)) < fabs(dsub(grid[lo], v))) ? hi : lo;
+}
+
 }  // namespace pb200

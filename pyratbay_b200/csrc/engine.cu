@@ -165,10 +165,20 @@ struct pb200_engine {
         V.doppler = d_doppler.p;
         V.nlor = nlor;
         V.ndop = ndop;
+        V.dop_hi0 = 0;
+        V.dop_inv_step = 0.f;
+        if (ndop >= 2 && doppler[0] > 0.0 && doppler[ndop - 1] > doppler[0]) {
+            long long bits;
+            std::memcpy(&bits, &doppler[0], sizeof(bits));
+            V.dop_hi0 = (int)(bits >> 32);
+            V.dop_inv_step = (float)((ndop - 1) / std::log2(doppler[ndop - 1] / doppler[0]) /
+                                     1048576.0);
+        }
         V.tprofile = d_tprofile.p;
         V.tbase = d_tbase.p;
         V.trow = d_trow.p;
         V.tstride = tstride;
+        V.fd_tstride.set(tstride > 0 ? tstride : 1);
         V.l_wn = d_lwn.p;
         V.l_elow = d_lelow.p;
         V.l_gf = d_lgf.p;
@@ -677,10 +687,20 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         U.mcount = 1 + (U.dnwn - 1) / U.scale;
         if (U.mcount > nwave) U.mcount = (int)nwave;
         U.out_index = u;
+        U.fd_ofactor.set(U.ofactor);
+        U.fd_scale.set(U.scale);
         for (int i = 0; i < niso; i++) {
             IsoUnit &I = iso_units[(size_t)u * niso + i];
+            // largest half-size among the Doppler samples lines inside the window can select
+            // (aD*wn is monotonic in wn; one extra sample either side for rounding safety)
+            const double *dg = e->doppler.data();
+            int n0 = nearest_bisect(dg, I.adop * own0, 0, ndop - 1) - 1;
+            int n1 = nearest_bisect(dg, I.adop * e->own[onwn - 1], 0, ndop - 1) + 1;
+            n0 = std::max(n0, 0);
+            n1 = std::min(n1, ndop - 1);
             int pmax = 0;
-            for (int n = 0; n < ndop; n++) pmax = std::max(pmax, e->psize[(size_t)I.ilor * ndop + n]);
+            for (int n = n0; n <= n1; n++)
+                pmax = std::max(pmax, e->psize[(size_t)I.ilor * ndop + n]);
             long long reach = pmax;
             if (cutoff > 0.0) reach = std::min<long long>(reach, (long long)(cutoff / ownstep) + 1);
             reach += 2LL * ofactor + 2;
@@ -734,11 +754,15 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         if (rc) return rc;
         d_out = e->d_out.p;
     }
-    size_t free_b = 0, total_b = 0;
-    PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget = (size_t)(0.6 * (double)(free_b + sizeof(double) * e->d_ksum.n));
     const size_t per_tp = sizeof(double) * (size_t)std::max<int64_t>(e->ngroups, 1);
-    int tp_chunk = (int)std::min<size_t>((size_t)ntp, std::max<size_t>(1, budget / per_tp));
+    int tp_chunk = ntp;
+    if (e->d_ksum.n * sizeof(double) < per_tp * (size_t)ntp) {
+        // the strengths scratch has to grow: size it against what is free right now
+        size_t free_b = 0, total_b = 0;
+        PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t budget = (size_t)(0.6 * (double)(free_b + sizeof(double) * e->d_ksum.n));
+        tp_chunk = (int)std::min<size_t>((size_t)ntp, std::max<size_t>(1, budget / per_tp));
+    }
     if (tp_chunk > 65535) tp_chunk = 65535;
 
     rc = e->d_ksum.alloc((size_t)tp_chunk * (size_t)std::max<int64_t>(e->ngroups, 1));

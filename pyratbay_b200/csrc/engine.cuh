@@ -9,6 +9,36 @@ namespace pb200 {
 constexpr int kTileOutputs = 256;  // output samples owned by one CTA of the accumulate kernel
 constexpr int kMaxIso = 256;
 
+// Exact division of a non-negative 31-bit integer by a launch-invariant divisor with one
+// multiply-high and one shift (Granlund-Montgomery round-up magic numbers).
+struct FastDiv {
+    unsigned mul = 0, shr = 0;
+    int d = 1;
+    void set(int denom) {
+        d = denom;
+        if (denom <= 1) { mul = 0; shr = 0; d = 1; return; }
+        unsigned lg = 0;
+        while ((1ull << lg) < (unsigned long long)denom) lg++;  // ceil(log2(denom))
+        const unsigned p = 31 + lg;
+        mul = (unsigned)(((1ull << p) + (unsigned)denom - 1) / (unsigned)denom);
+        shr = p - 32;
+    }
+#ifdef __CUDACC__
+    __device__ __forceinline__ int div(int n) const {  // 0 <= n < 2^31
+        return d == 1 ? n : (int)(__umulhi((unsigned)n, mul) >> shr);
+    }
+    __device__ __forceinline__ int div_trunc(int n) const {  // C semantics, any sign
+        return n >= 0 ? div(n) : -div(-n);
+    }
+    __device__ __forceinline__ int div_ceil(int n) const {  // n >= 0
+        return div(n + d - 1);
+    }
+    __device__ __forceinline__ int div_floor(int n) const {  // any sign
+        return n >= 0 ? div(n) : -div(-n + d - 1);
+    }
+#endif
+};
+
 // Device view of everything that does not depend on (T,p).  Passed to kernels by value.
 struct StaticView {
     // spectral grids
@@ -22,6 +52,8 @@ struct StaticView {
     const long long *pindex;   // [nlor*ndop] start index
     const double *doppler;     // [ndop]
     int nlor, ndop;
+    int dop_hi0;               // high word of doppler[0]            (nearest_index_log)
+    float dop_inv_step;        // (ndop-1)/log2(doppler[-1]/doppler[0])/2^20
     // Output-stride ("transposed") copy of the Voigt table for constant-step output grids:
     // profile p is stored as rows of every tstride-th sample, T[r][q] = profile[q*tstride+r],
     // so the samples one line contributes to consecutive output points are contiguous.
@@ -29,6 +61,7 @@ struct StaticView {
     const long long *tbase;    // [nlor*ndop] start of the profile's transposed block
     const int *trow;           // [nlor*ndop] row length Q = ceil((2*size+1)/tstride)
     int tstride;               // fine samples per output sample (0: no transposed copy)
+    FastDiv fd_tstride;
     // co-add groups (sorted by isotope, then wavenumber)
     const double *l_wn, *l_elow, *l_gf;   // in-window lines, member order
     const double *g_wn;                   // head-line wavenumber
@@ -53,6 +86,7 @@ struct UnitParams {
     int dnwn;          // dynamic samples                 (:195)
     int mcount;        // resampled outputs written       (utils.h:130)
     int out_index;     // position of this unit in the caller's batch
+    FastDiv fd_ofactor, fd_scale;
 };
 
 struct IsoUnit {

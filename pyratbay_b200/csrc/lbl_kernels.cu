@@ -34,12 +34,6 @@ struct Prep {
     int lo, hi;      // coordinate range [lo, hi): dynamic index j, or output index m (kTransposed)
 };
 
-__device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
-    int q = a / b;
-    return (a % b < 0) ? q - 1 : q;
-}
-__device__ __forceinline__ int ceil_div_nonneg(int a, int b) { return (a + b - 1) / b; }
-
 // The per-group part of _extcoeff.c:264-299, identical integer/floating-point decisions.
 template <int MODE>
 __device__ __forceinline__ bool prepare_group(const StaticView &V, const UnitParams &U,
@@ -49,12 +43,14 @@ __device__ __forceinline__ bool prepare_group(const StaticView &V, const UnitPar
     if (k < kthr) return false;  // :265 skip weak lines
     k = dmul(k, I.dens);         // :271-272 (dens == 1 when add == 0)
     const int idwn = (int)ddiv(dsub(w, V.own0), U.dwnstep);                 // :275
-    const int idop = nearest_index(s_doppler, V.ndop, dmul(I.adop, w));     // :278
+    const int idop = (V.ndop >= 2)                                          // :278
+        ? nearest_index_log(s_doppler, V.ndop, dmul(I.adop, w), V.dop_hi0, V.dop_inv_step)
+        : 0;
     const int at = I.ilor * V.ndop + idop;
     const int half = V.psize[at];
     const int sub = iown - idwn * U.ofactor;                                // :281
-    int jlo = idwn - (half - sub) / U.ofactor;                              // :286
-    int jhi = idwn + (half + sub) / U.ofactor;                              // :287
+    int jlo = idwn - U.fd_ofactor.div_trunc(half - sub);                    // :286
+    int jhi = idwn + U.fd_ofactor.div_trunc(half + sub);                    // :287
     if (jlo < 0) jlo = 0;
     if (jhi > U.dnwn) jhi = U.dnwn;
     if (cutoff > 0.0) {                                                     // :294-299
@@ -66,12 +62,12 @@ __device__ __forceinline__ bool prepare_group(const StaticView &V, const UnitPar
     out->k = k;
     if (MODE == kTransposed) {
         // outputs m with scale*m in [jlo, jhi), m < mcount            (utils.h:130-133)
-        int mlo = ceil_div_nonneg(jlo, U.scale);
-        int mhi = jhi > 0 ? ceil_div_nonneg(jhi, U.scale) : 0;
+        int mlo = U.fd_scale.div_ceil(jlo);
+        int mhi = jhi > 0 ? U.fd_scale.div_ceil(jhi) : 0;
         if (mhi > U.mcount) mhi = U.mcount;
         // profile sample of output m: half - iown + tstride*m = q*tstride + r
         const int d = half - iown;
-        const int q0 = floor_div(d, V.tstride);
+        const int q0 = V.fd_tstride.div_floor(d);
         const int r = d - q0 * V.tstride;
         out->base = V.tbase[at] + (long long)r * V.trow[at] + q0;
         out->lo = mlo;
@@ -143,8 +139,9 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
                   const unsigned long long *__restrict__ kmax, int nrows, double ethresh,
                   double cutoff, double *__restrict__ out) {
     extern __shared__ double s_doppler[];  // [ndop]
-    __shared__ double s_k[8][32];
-    __shared__ long long s_base[8][32];
+    // One staged group per lane: {k, byte address of its sample for coordinate 0} and
+    // {first coordinate, number of coordinates}.
+    __shared__ double2 s_kp[8][32];
     __shared__ int2 s_r[8][32];
 
     for (int i = threadIdx.x; i < V.ndop; i += blockDim.x) s_doppler[i] = V.doppler[i];
@@ -176,6 +173,8 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
     int xmax = (x0 >= 0) ? (MODE == kLinterp ? x1 : x0) : INT_MIN;
     xmin = __reduce_min_sync(0xffffffffu, xmin);
     xmax = __reduce_max_sync(0xffffffffu, xmax);
+    // byte offset of this lane's sample(s) from a staged group's base address
+    const long long off0 = (long long)mult * x0 * 8, off1 = (long long)mult * x1 * 8;
 
     double acc0 = 0.0, acc1 = 0.0;
     if (xmax >= xmin) {
@@ -193,27 +192,51 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
             const int ghi = gb[(int)(fhi / V.binw) + 1];
             const double kthr =
                 dmul(ethresh, __longlong_as_double((long long)kmax[(size_t)U.tpass * nrows + row]));
+            // inputs of the first chunk; each later chunk's are requested one chunk ahead so
+            // that their latency overlaps the slot loop
+            double nx_w = 0.0, nx_k = 0.0;
+            int nx_iown = 0;
+            if (glo + lane < ghi) {
+                nx_w = V.g_wn[glo + lane];
+                nx_iown = V.g_iown[glo + lane];
+                nx_k = ks[glo + lane];
+            }
             for (int c = glo; c < ghi; c += 32) {
                 const int g = c + lane;
+                const double cur_w = nx_w, cur_k = nx_k;
+                const int cur_iown = nx_iown;
+                if (g + 32 < ghi) {
+                    nx_w = V.g_wn[g + 32];
+                    nx_iown = V.g_iown[g + 32];
+                    nx_k = ks[g + 32];
+                }
                 Prep p;
                 p.k = 0.0; p.base = 0; p.lo = 0; p.hi = 0;
                 if (g < ghi)
-                    prepare_group<MODE>(V, U, I, s_doppler, kthr, cutoff, V.g_wn[g], V.g_iown[g],
-                                        ks[g], &p);
-                s_k[warp][lane] = p.k;
-                s_base[warp][lane] = p.base;
-                s_r[warp][lane] = make_int2(p.lo, p.hi);
+                    prepare_group<MODE>(V, U, I, s_doppler, kthr, cutoff, cur_w, cur_iown, cur_k,
+                                        &p);
+                // clip to the coordinates this warp owns so that empty slots cost nothing more
+                const int lo = max(p.lo, xmin), hi = min(p.hi, xmax + 1);
+                s_kp[warp][lane] = make_double2(
+                    p.k, __longlong_as_double((long long)(table + p.base)));
+                s_r[warp][lane] = make_int2(lo, hi > lo ? hi - lo : 0);
                 __syncwarp();
                 const int n = min(32, ghi - c);
+#pragma unroll 8
                 for (int t = 0; t < n; t++) {
                     const int2 r = s_r[warp][t];
-                    if (r.y <= xmin || r.x > xmax) continue;  // warp-uniform
-                    const double k = s_k[warp][t];
-                    const long long base = s_base[warp][t];
-                    if (x0 >= r.x && x0 < r.y)
-                        acc0 = fma(k, __ldg(table + base + (long long)mult * x0), acc0);
-                    if (MODE == kLinterp && x1 >= r.x && x1 < r.y)
-                        acc1 = fma(k, __ldg(table + base + (long long)mult * x1), acc1);
+                    if ((unsigned)(x0 - r.x) < (unsigned)r.y) {
+                        const double2 kp = s_kp[warp][t];
+                        const double *src =
+                            (const double *)(__double_as_longlong(kp.y) + off0);
+                        acc0 = fma(kp.x, __ldg(src), acc0);
+                    }
+                    if (MODE == kLinterp && (unsigned)(x1 - r.x) < (unsigned)r.y) {
+                        const double2 kp = s_kp[warp][t];
+                        const double *src =
+                            (const double *)(__double_as_longlong(kp.y) + off1);
+                        acc1 = fma(kp.x, __ldg(src), acc1);
+                    }
                 }
                 __syncwarp();
             }
