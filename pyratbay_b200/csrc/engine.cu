@@ -114,7 +114,7 @@ struct pb200_engine {
     std::vector<long long> pindex;
     int64_t profile_len = 0;
     DevBuf<double> d_profile, d_doppler;
-    DevBuf<int> d_psize;
+    DevBuf<int> d_psize, d_pmaxrow;
     DevBuf<long long> d_pindex;
     // output-stride copy of the table (built on first use for constant-step output grids)
     int tstride = 0;
@@ -162,6 +162,12 @@ struct pb200_engine {
         V.profile = d_profile.p;
         V.psize = d_psize.p;
         V.pindex = d_pindex.p;
+        V.pmaxrow = d_pmaxrow.p;
+        V.cut_fine = 0x7fffffff;
+        if (cutoff > 0.0 && own.size() > 1) {
+            const double c = cutoff / (own[1] - own[0]) + 1.0;
+            if (c < 2.0e9) V.cut_fine = (int)c;
+        }
         V.doppler = d_doppler.p;
         V.nlor = nlor;
         V.ndop = ndop;
@@ -307,7 +313,16 @@ static int adopt_voigt_tables(pb200_engine *e, int nlor, int ndop, const double 
         e->psize[i] = (int)psize[i];
         e->pindex[i] = (long long)pindex[i];
     }
+    std::vector<int> pmaxrow(e->psize.size());
+    for (int m = 0; m < nlor; m++) {
+        int best = 0;
+        for (int n = 0; n < ndop; n++) {
+            best = std::max(best, e->psize[(size_t)m * ndop + n]);
+            pmaxrow[(size_t)m * ndop + n] = best;
+        }
+    }
     int rc = e->d_psize.upload(e->psize.data(), e->psize.size(), e->stream);
+    if (!rc) rc = e->d_pmaxrow.upload(pmaxrow.data(), pmaxrow.size(), e->stream);
     if (!rc) rc = e->d_pindex.upload(e->pindex.data(), e->pindex.size(), e->stream);
     if (!rc) rc = e->d_doppler.upload(doppler, (size_t)ndop, e->stream);
     if (rc) return rc;

@@ -50,6 +50,8 @@ struct StaticView {
     const double *profile;
     const int *psize;          // [nlor*ndop] half sizes (aliases resolved)
     const long long *pindex;   // [nlor*ndop] start index
+    const int *pmaxrow;        // [nlor*ndop] running maximum of psize along the Doppler axis
+    int cut_fine;              // cutoff in fine samples (+1), INT_MAX when there is no cutoff
     const double *doppler;     // [ndop]
     int nlor, ndop;
     int dop_hi0;               // high word of doppler[0]            (nearest_index_log)

@@ -182,8 +182,20 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
         for (int iso = 0; iso < V.niso; iso++) {
             if (iso_row[iso] != row) continue;
             const IsoUnit I = iso_units[(size_t)blockIdx.y * V.niso + iso];
-            long long flo = (long long)xmin * fstride - I.reach;
+            // Candidate window: first with the unit-wide reach, then tightened with the
+            // largest profile any line up to the window's upper end can select (the Doppler
+            // index grows with wavenumber; pmaxrow is the running maximum along that axis).
             long long fhi = (long long)xmax * fstride + I.reach;
+            int reach = I.reach;
+            if (V.ndop >= 2) {
+                const double wn_hi = dadd(V.own0, dmul((double)min(fhi, V.onwn - 1), V.ownstep));
+                const int nhi = min(V.ndop - 1, 1 + nearest_index_log(
+                    s_doppler, V.ndop, dmul(I.adop, wn_hi), V.dop_hi0, V.dop_inv_step));
+                reach = min(reach, min(V.pmaxrow[I.ilor * V.ndop + nhi], V.cut_fine) +
+                                       2 * U.ofactor + 2);
+            }
+            long long flo = (long long)xmin * fstride - reach;
+            fhi = (long long)xmax * fstride + reach;
             if (fhi < 0 || flo > V.onwn - 1) continue;
             if (flo < 0) flo = 0;
             if (fhi > V.onwn - 1) fhi = V.onwn - 1;
