@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libpb200_lbl.so")
+# PB200_LIB selects an alternative build of the same library (kernel-tuning experiments).
+_LIB_PATH = os.environ.get("PB200_LIB") or os.path.join(_HERE, "libpb200_lbl.so")
 _lib = None
 
 c_double_p = ctypes.POINTER(ctypes.c_double)

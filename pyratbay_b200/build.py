@@ -39,13 +39,15 @@ def needs_build():
     return os.path.getmtime(out) < newest
 
 
-def build_library(force=False, verbose=False):
-    """Compile csrc/*.cu into libpb200_lbl.so.  Returns the library path."""
-    out = lib_path()
-    if not force and not needs_build():
+def build_library(force=False, verbose=False, defines=(), out=None):
+    """Compile csrc/*.cu into libpb200_lbl.so.  Returns the library path.
+    `defines` / `out` build a tuning variant (e.g. defines=["PB200_UNROLL=4"])."""
+    variant = out is not None
+    out = out or lib_path()
+    if not variant and not force and not needs_build():
         return out
     csrc = os.path.join(_HERE, "csrc")
-    cmd = [_nvcc()] + NVCC_FLAGS
+    cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(csrc, s) for s in SOURCES] + ["-o", out]

@@ -131,8 +131,19 @@ strengths_kernel(StaticView V, const double *__restrict__ tp_temp,
 
 // ---------------------------------------------------------------------------------------
 // Kernel 3: output-owned accumulation.  grid = (tiles, units, rows), 256 threads.
+#ifndef PB200_UNROLL
+#define PB200_UNROLL 8
+#endif
+#ifdef PB200_MINBLOCKS
+#define PB200_ACC_BOUNDS __launch_bounds__(256, PB200_MINBLOCKS)
+#else
+#define PB200_ACC_BOUNDS __launch_bounds__(256)  // 56 registers -> 4 CTAs/SM (measured best)
+#endif
+#define PB200_STR2(x) #x
+#define PB200_STR(x) PB200_STR2(x)
+#define PB200_PRAGMA_UNROLL _Pragma(PB200_STR(unroll PB200_UNROLL))
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void PB200_ACC_BOUNDS
 accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
                   const IsoUnit *__restrict__ iso_units, const int *__restrict__ iso_row,
                   const double *__restrict__ ksum,
@@ -234,7 +245,7 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
                 s_r[warp][lane] = make_int2(lo, hi > lo ? hi - lo : 0);
                 __syncwarp();
                 const int n = min(32, ghi - c);
-#pragma unroll 8
+PB200_PRAGMA_UNROLL
                 for (int t = 0; t < n; t++) {
                     const int2 r = s_r[warp][t];
                     if ((unsigned)(x0 - r.x) < (unsigned)r.y) {
