@@ -105,7 +105,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.device)],
+                 "-lms", "25", "-i", str(self.device)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -157,6 +157,7 @@ def run_b200(args):
         raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from pyratbay_b200 import workloads
@@ -245,6 +246,7 @@ def run_b200(args):
     neval = int(cnt[:, 2].sum())
     dyn_samples = int(cnt[:, 3].sum())
     gathered = int(cnt[:, 4].sum())
+    table_bytes = int(cnt[:, 5].sum())
     checksum = float(d_out.sum().item())
 
     if rank != 0:
@@ -256,20 +258,25 @@ def run_b200(args):
     value = contributions * world / (ms_per_step * 1e-3)
     e2e_value = contributions * world / (e2e_ms / args.steps * 1e-3)
 
-    # Roofline of the dominant kernel (accumulate).  Algorithmic HBM bytes per launch
-    # (DESIGN.md section 5): 20 B per evaluated group (k, head wavenumber, fine index) plus
-    # 8 B per output sample.
+    # Roofline of the dominant kernel (accumulate); DESIGN.md section 5 has the derivation.
+    # Algorithmic HBM bytes per launch = per (T,p) unit: 20 B per evaluated group (k, head
+    # wavenumber, fine index) + 8 B per output sample + the distinct
+    # Voigt-table samples the unit's lines select (each unit has its own Lorentz width, so
+    # its profiles are read from HBM once and then gathered from L2).
     hbm_peak, peak_src = measured_peaks()
-    algo_bytes = 20.0 * neval + 8.0 * nlayers * nwave
+    group_out_bytes = 20.0 * neval + 8.0 * nlayers * nwave
+    algo_bytes = group_out_bytes + table_bytes
     achieved = algo_bytes / (acc_ms * 1e-3) / 1e9
     fp64_tf, l2_gbs = device_ceilings(local_rank)
-    roofline = {"bound": "hbm", "kernel": "accumulate_kernel<false>", "achieved": achieved,
-                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": acc_ms,
-                "share_of_step": acc_ms / ms_per_step,
-                "note": "gather-bound on L2-resident Voigt samples, not on HBM; see "
-                        "roofline_l2 / roofline_fp64"}
+    roofline = {"bound": "hbm", "kernel": "accumulate_kernel<kTransposed>",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "algorithmic_bytes_groups_and_output": group_out_bytes,
+                "algorithmic_bytes_voigt_table_first_touch": float(table_bytes),
+                "launch_ms": acc_ms, "share_of_step": acc_ms / ms_per_step,
+                "note": "traffic (ncu dram bytes) is in profiles/; the kernel is issue/latency "
+                        "bound, see roofline_l2 / roofline_fp64 for the other ceilings"}
     roofline_l2 = {"bound": "l2", "achieved": 8.0 * gathered / (acc_ms * 1e-3) / 1e9,
                    "peak": l2_gbs, "unit": "GB/s",
                    "frac": 8.0 * gathered / (acc_ms * 1e-3) / 1e9 / l2_gbs,

@@ -125,10 +125,11 @@ int pb200_engine_line_stats(const pb200_engine *e, int64_t stats[3]);
  *   out           [n_units, nrows, nwave]; OVERWRITTEN with what the reference would
  *                 leave in a zero-initialised `ext` (every reference call site zeroes it:
  *                 pyrat/extinction.py:195).
- *   counters      NULL or [n_units, 5] int64: nadd, nskip, neval (the reference's verbose
+ *   counters      NULL or [n_units, 6] int64: nadd, nskip, neval (the reference's verbose
  *                 counters, _extcoeff.c:311-318), the dynamic-grid samples the reference
- *                 accumulates for this unit (sum of maxj-minj, :304-307) and the profile
- *                 samples this engine gathers for it.
+ *                 accumulates for this unit (sum of maxj-minj, :304-307), the profile
+ *                 samples this engine gathers for it, and the bytes of distinct Voigt-table
+ *                 samples the unit's lines can select (first-touch HBM traffic).
  * The *_host form copies inputs/outputs itself; the *_dev form takes `out` as a device
  * pointer (e.g. a torch tensor's data_ptr) and leaves the result on the device. */
 int pb200_extinction_batch_host(pb200_engine *e, int n_units, const double *unit_temp,

@@ -664,6 +664,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
     std::map<std::vector<double>, int> tp_index;
     std::vector<double> tp_temp, tp_isoz;
     std::vector<int> unit_tp(n_units);
+    std::vector<long long> unit_table_bytes(n_units, 0);
     for (int u = 0; u < n_units; u++) {
         const double temp = unit_temp[u];
         const double *dens = unit_density + (size_t)u * nmol;
@@ -714,8 +715,20 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
             n0 = std::max(n0, 0);
             n1 = std::min(n1, ndop - 1);
             int pmax = 0;
-            for (int n = n0; n <= n1; n++)
-                pmax = std::max(pmax, e->psize[(size_t)I.ilor * ndop + n]);
+            long long last_index = -1;
+            for (int n = n0; n <= n1; n++) {
+                const size_t at = (size_t)I.ilor * ndop + n;
+                pmax = std::max(pmax, e->psize[at]);
+                // distinct table samples within the cutoff window that this unit's lines of
+                // this isotope can read (roofline accounting only)
+                if (iso_row[i] >= 0 && e->pindex[at] != last_index) {
+                    long long span = 2LL * e->psize[at] + 1;
+                    if (cutoff > 0.0)
+                        span = std::min<long long>(span, 2LL * (long long)(cutoff / ownstep) + 1);
+                    unit_table_bytes[u] += 8 * span;
+                    last_index = e->pindex[at];
+                }
+            }
             long long reach = pmax;
             if (cutoff > 0.0) reach = std::min<long long>(reach, (long long)(cutoff / ownstep) + 1);
             reach += 2LL * ofactor + 2;
@@ -890,11 +903,12 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         for (int i = 0; i < niso; i++)
             if (iso_row[i] >= 0) nadd += e->iso_nadd[i];
         for (int u = 0; u < n_units; u++) {
-            counters[(size_t)u * 5 + 0] = nadd;
-            counters[(size_t)u * 5 + 1] = (int64_t)cnt[(size_t)u * 4 + 0];
-            counters[(size_t)u * 5 + 2] = (int64_t)cnt[(size_t)u * 4 + 1];
-            counters[(size_t)u * 5 + 3] = (int64_t)cnt[(size_t)u * 4 + 2];
-            counters[(size_t)u * 5 + 4] = (int64_t)cnt[(size_t)u * 4 + 3];
+            counters[(size_t)u * 6 + 0] = nadd;
+            counters[(size_t)u * 6 + 1] = (int64_t)cnt[(size_t)u * 4 + 0];
+            counters[(size_t)u * 6 + 2] = (int64_t)cnt[(size_t)u * 4 + 1];
+            counters[(size_t)u * 6 + 3] = (int64_t)cnt[(size_t)u * 4 + 2];
+            counters[(size_t)u * 6 + 4] = (int64_t)cnt[(size_t)u * 4 + 3];
+            counters[(size_t)u * 6 + 5] = (int64_t)unit_table_bytes[u];
         }
     }
     float t_all = 0.f, t_d2h = 0.f;

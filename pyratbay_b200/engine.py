@@ -196,7 +196,7 @@ class Engine:
         z = None if isoz is None else _f64(isoz).reshape(n_units, self.niso)
         ie = _i64(iso_iext)
         nrows = 1 if add else int(nextinct)
-        cnt = np.zeros((n_units, 5), np.int64) if counters else None
+        cnt = np.zeros((n_units, 6), np.int64) if counters else None
         cnt_p = _ip(cnt) if counters else None
         z_p = _dp(z) if z is not None else None
         if out_device_ptr is not None:
