@@ -41,6 +41,10 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nlines", type=int, default=1_000_000)
     ap.add_argument("--nlayers", type=int, default=81)
+    ap.add_argument("--wl-low", type=float, default=0.5, help="um")
+    ap.add_argument("--wl-high", type=float, default=5.0, help="um")
+    ap.add_argument("--ptop", type=float, default=1e-6, help="bar")
+    ap.add_argument("--pbottom", type=float, default=100.0, help="bar")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-layers", type=int, default=0)
     return ap.parse_args()
@@ -167,7 +171,8 @@ def run_b200(args):
 
     # Static set-up (not timed): TLI file -> Pyrat-shaped objects -> engine on this GPU.
     t_setup = time.time()
-    w = workloads.forward_model_workload(args.nlines, args.nlayers)
+    w = workloads.forward_model_workload(args.nlines, args.nlayers, args.wl_low, args.wl_high,
+                                         ptop=args.ptop, pbottom=args.pbottom)
     tli_path = f"/tmp/pb200_bench_{args.nlines}_{rank}.tli"
     ptli.write_tli(tli_path, [w.db], [{
         "wn": w.wn, "elow": w.elow, "gf": w.gf, "iso_id": w.isoid,

@@ -14,20 +14,20 @@ UNIFORM_SPECIES = ['H2', 'He', 'H', 'Na', 'K', 'H2O', 'CH4', 'CO', 'CO2']
 UNIFORM_VMR = [8.5e-01, 1.49e-01, 1.0e-06, 3.0e-06, 5.0e-08, 4.0e-04, 1.0e-04, 5.0e-04, 1.0e-07]
 
 
-def layer_temperatures(nlayers, realization=0):
-    """Smooth T(p): 800 K at the top to 2200 K at the bottom, linear in log p, plus a small
+def layer_temperatures(nlayers, realization=0, ttop=800.0, tbottom=2200.0):
+    """Smooth T(p): `ttop` at the top to `tbottom` at the bottom, linear in log p, plus a small
     realization-dependent offset (a retrieval evaluates a new profile every step)."""
-    base = np.linspace(800.0, 2200.0, nlayers)
+    base = np.linspace(ttop, tbottom, nlayers)
     return base + 0.37 * (realization % 97)
 
 
 def forward_model_workload(nlines=1_000_000, nlayers=81, wl_low_um=0.5, wl_high_um=5.0,
-                           wnstep=1.0, wnosamp=2160, seed=0):
+                           wnstep=1.0, wnosamp=2160, seed=0, ptop=1e-6, pbottom=100.0):
     """configs[1]: synthetic H2O line list, `nlayers`-layer atmosphere 1e-6..100 bar,
     forward-model extinction (add=1) on a constant-step wavenumber grid."""
     spec = Spectrum(wl_low=wl_low_um * pc.um, wl_high=wl_high_um * pc.um, wnstep=wnstep,
                     wnosamp=wnosamp)
-    press = pa.pressure(1e-6, 100.0, nlayers)
+    press = pa.pressure(ptop, pbottom, nlayers)
     vmr = np.tile(np.asarray(UNIFORM_VMR), (nlayers, 1))
     atm = pa.Atmosphere(press, layer_temperatures(nlayers), vmr, UNIFORM_SPECIES)
     db = ptli.synthetic_h2o_database()

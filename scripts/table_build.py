@@ -1,0 +1,149 @@
+#!/usr/bin/env python
+"""Cross-section table build at scale (BASELINE.json configs[2]): synthetic H2O line list,
+ntemp x nlayers (T,p) units, constant-step wavenumber grid, one process per GPU.
+
+    python scripts/table_build.py --nlines 1e8 --ntemp 20 --nlayers 51 --nwave 100000
+    torchrun --nproc-per-node 8 scripts/table_build.py ...      # units sharded over ranks
+
+Prints one JSON line (rank 0): set-up times, table build time, line x layer/s, and (optional)
+a parity spot-check of a few units against the CPU oracle on a line subsample is left to the
+tests; this script checks only size-independent properties (finite, non-negative, symmetric
+shard assembly).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nlines", type=float, default=1e7)
+    ap.add_argument("--ntemp", type=int, default=20)
+    ap.add_argument("--nlayers", type=int, default=51)
+    ap.add_argument("--nwave", type=int, default=100000)
+    ap.add_argument("--wl-low", type=float, default=0.3)
+    ap.add_argument("--wl-high", type=float, default=30.0)
+    ap.add_argument("--tmin", type=float, default=300.0)
+    ap.add_argument("--tmax", type=float, default=3000.0)
+    ap.add_argument("--out", default=None, help="write the .npz table here (rank 0)")
+    ap.add_argument("--gather", action="store_true", help="all-gather the table over NCCL")
+    args = ap.parse_args()
+    nlines = int(args.nlines)
+
+    import torch
+    import torch.distributed as dist
+    from pyratbay_b200 import atmosphere as pa, constants as pc, io, parallel, tli as ptli
+    from pyratbay_b200 import workloads
+    from pyratbay_b200.engine import Engine
+    from pyratbay_b200.spectrum import Spectrum, _HCN
+    from pyratbay_b200.voigt import Voigt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    t = {}
+    t0 = time.time()
+    wnlow, wnhigh = 1.0 / (args.wl_high * pc.um), 1.0 / (args.wl_low * pc.um)
+    wnstep = (wnhigh - wnlow) / (args.nwave - 1)
+    wnosamp = int(_HCN[wnstep / _HCN <= 0.0004][0])
+    spec = Spectrum(wnlow=wnlow, wnhigh=wnhigh, wnstep=wnstep, wnosamp=wnosamp)
+    press = pa.pressure(1e-6, 100.0, args.nlayers)
+    vmr = np.tile(np.asarray(workloads.UNIFORM_VMR), (args.nlayers, 1))
+    atm = pa.Atmosphere(press, np.full(args.nlayers, 1000.0), vmr, workloads.UNIFORM_SPECIES)
+    db = ptli.synthetic_h2o_database()
+    wn, elow, gf, iso, _ = ptli.synthetic_lines(nlines, spec.wnlow, spec.wnhigh, seed=0)
+    t["host_lines_s"] = time.time() - t0
+
+    t0 = time.time()
+    eng = Engine(local_rank)
+    eng.set_grid(spec.wn, spec.own, spec.odivisors)
+    iso_atm_index = np.full(db.niso, workloads.UNIFORM_SPECIES.index("H2O"), int)
+    eng.set_species(atm.mol_radius, atm.mol_mass, iso_atm_index, db.iso_mass, db.iso_ratio)
+    t["grid_species_s"] = time.time() - t0
+    t0 = time.time()
+    eng.set_lines(wn, elow, gf, iso.astype(np.int64))
+    t["set_lines_s"] = time.time() - t0
+    stats = eng.line_stats()
+    del wn, elow, gf, iso
+    t0 = time.time()
+    voigt = Voigt(spec, atm, iso_atm_index, eng, tmin=args.tmin, tmax=args.tmax)
+    torch.cuda.synchronize()
+    t["voigt_s"] = time.time() - t0
+
+    temps = np.linspace(args.tmin, args.tmax, args.ntemp)
+    z = workloads.partition(db, temps)                     # [ntemp, niso]
+    n_units = args.ntemp * args.nlayers
+    mine = parallel.partition_units(n_units, rank, world)
+    itemp, ilayer = mine // args.nlayers, mine % args.nlayers
+    unit_t = temps[itemp]
+    dens = atm.vmr[ilayer] * press[ilayer, None] * pc.bar / (pc.k * unit_t[:, None])
+    d_out = torch.empty((len(mine), 1, spec.nwave), dtype=torch.float64,
+                        device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    eng.extinction_batch(unit_t, dens, z[itemp], np.zeros(db.niso, int), 1, 1e-30, 0, 0,
+                         out_device_ptr=d_out.data_ptr())
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    tim = eng.last_timing()
+    build = torch.tensor([build_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(build, op=dist.ReduceOp.MAX)
+    finite = bool(torch.isfinite(d_out).all().item()) and bool((d_out >= 0).all().item())
+    checksum = float(d_out.sum().item())
+
+    gather_s = None
+    table = None
+    if args.gather or args.out:
+        t0 = time.time()
+        if world > 1:
+            counts = [len(parallel.partition_units(n_units, r, world)) for r in range(world)]
+            pad = max(counts)
+            local = torch.zeros((pad, spec.nwave), dtype=torch.float64, device=d_out.device)
+            local[:len(mine)] = d_out[:, 0]
+            full = torch.empty((world * pad, spec.nwave), dtype=torch.float64, device=d_out.device)
+            dist.all_gather_into_tensor(full, local)
+            torch.cuda.synchronize()
+            table = torch.empty((n_units, spec.nwave), dtype=torch.float64, device=d_out.device)
+            for r in range(world):
+                idx = torch.from_numpy(parallel.partition_units(n_units, r, world)).to(d_out.device)
+                table[idx] = full[r * pad:r * pad + len(idx)]
+        else:
+            table = d_out[:, 0]
+        torch.cuda.synchronize()
+        gather_s = time.time() - t0
+    if rank == 0:
+        if args.out:
+            io.write_opacity(args.out, "H2O", temps, press, spec.wn,
+                             table.cpu().numpy().reshape(args.ntemp, args.nlayers, spec.nwave))
+        contributions = stats["in_window"] * n_units
+        print(json.dumps({
+            "workload": f"table {nlines:.0e} lines x {args.ntemp} T x {args.nlayers} p x "
+                        f"{spec.nwave} wn ({args.wl_low}-{args.wl_high} um, wnosamp {wnosamp})",
+            "n_gpus": world, "units_per_gpu": len(mine), "groups": stats["groups"],
+            "nadd": stats["nadd"], "build_s": float(build.item()),
+            "line_layer_per_s": contributions / float(build.item()),
+            "strengths_ms": tim["strengths_ms"], "accumulate_ms": tim["accumulate_ms"],
+            "voigt_samples": eng.profile_len(), "gather_s": gather_s, "finite_nonneg": finite,
+            "checksum_rank0": checksum, "setup": t, "onwave": int(spec.onwave),
+            "mem_GB": torch.cuda.max_memory_allocated() / 1e9}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
