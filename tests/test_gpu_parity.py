@@ -340,3 +340,67 @@ def test_line_sample_matches_reference():
                                g["ec_layer"], rtol=1e-14)
     with pytest.raises(ValueError):
         ls.calc_cross_section(np.full(ls.nlayers, 5000.0))
+
+
+# ------------------------------------------------------------- full-size configs[1] checks
+@pytest.fixture(scope="module")
+def full_size_engine():
+    """BASELINE.json configs[1]: 1e6 synthetic H2O lines, 81 layers, 0.5-5 um, add=1."""
+    from pyratbay_b200 import workloads
+    from pyratbay_b200.engine import Engine
+    from pyratbay_b200.voigt import Voigt
+    w = workloads.forward_model_workload(1_000_000, 81)
+    eng = Engine(0)
+    eng.set_grid(w.spec.wn, w.spec.own, w.spec.odivisors)
+    eng.set_species(w.atm.mol_radius, w.atm.mol_mass, w.iso_atm_index, w.db.iso_mass,
+                    w.db.iso_ratio)
+    eng.set_lines(w.wn, w.elow, w.gf, w.isoid)
+    voigt = Voigt(w.spec, w.atm, w.iso_atm_index, eng)
+    temps = w.atm.temp
+    isoz = workloads.partition(w.db, temps)
+    yield w, eng, voigt, temps, isoz
+    eng.close()
+
+
+def test_full_size_spot_check_against_oracle(full_size_engine):
+    """Three of the 81 layers of the benchmark workload, every line, against the CPU oracle
+    (low, middle and high pressure: narrow, mixed and Lorentz-dominated profiles)."""
+    w, eng, voigt, temps, isoz = full_size_engine
+    orc = helpers.oracle_module()
+    got, cnt = eng.extinction_batch(temps, w.atm.d, isoz, w.iso_mol_index, 1, 1e-30, 1, 0,
+                                    counters=True)
+    assert np.all(np.isfinite(got)) and np.all(got >= 0)
+    profile = voigt.profile     # device table copied back; the oracle reads the same table
+    for layer in (3, 40, 80):
+        ext = np.zeros((1, w.spec.nwave))
+        ocnt = np.zeros(4, np.int64)
+        orc.extinction(ext, profile, voigt.size, voigt.index, voigt.lorentz, voigt.doppler,
+                       w.spec.wn, w.spec.own, w.spec.odivisors, w.atm.d[layer],
+                       w.atm.mol_radius, w.atm.mol_mass, w.iso_atm_index, w.db.iso_mass,
+                       w.db.iso_ratio, isoz[layer], w.iso_mol_index, w.wn, w.elow, w.gf,
+                       w.isoid, voigt.cutoff, 1e-30, temps[layer], 0, 1, 0, counters=ocnt)
+        assert np.array_equal(cnt[layer, :4], ocnt)
+        assert _peak_err(got[layer], ext) < TOL_PEAK
+
+
+def test_full_size_exact_linearity_and_isotope_additivity(full_size_engine):
+    """Size-independent properties at the benchmark size.
+    (1) Doubling every gf doubles every strength exactly (power of two), leaves the ethresh
+        selection unchanged and so must double the output BIT FOR BIT.
+    (2) Co-add groups never span isotopes, so the extinction of all isotopes equals the sum
+        of the four single-isotope runs (summation order aside)."""
+    w, eng, voigt, temps, isoz = full_size_engine
+    args = (temps, w.atm.d, isoz)
+    base = eng.extinction_batch(*args, w.iso_mol_index, 1, 1e-30, 1, 0)
+    parts = np.zeros_like(base)
+    for i in range(w.db.niso):
+        iext = np.full(w.db.niso, -1)
+        iext[i] = 0
+        parts += eng.extinction_batch(*args, iext, 1, 1e-30, 1, 0)
+    assert _peak_err(parts, base) < 1e-12
+    eng.set_lines(w.wn, w.elow, 2.0 * w.gf, w.isoid)
+    doubled = eng.extinction_batch(*args, w.iso_mol_index, 1, 1e-30, 1, 0)
+    eng.set_lines(w.wn, w.elow, w.gf, w.isoid)
+    assert np.array_equal(doubled, 2.0 * base)
+    # checksum of checksums: per-layer sums add up to the grand total
+    assert abs(np.sum(np.sum(base, axis=-1)) / np.sum(base) - 1.0) < 1e-13
