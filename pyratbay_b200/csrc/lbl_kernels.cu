@@ -96,19 +96,16 @@ strengths_kernel(StaticView V, const double *__restrict__ tp_temp,
         row = iso_row[iso];
         double k = 0.0;
         if (row >= 0) {
-            // The two divisions by T and the one by Z are done as multiplications by
-            // reciprocals taken once per thread (what the reference's -ffast-math build does
-            // too); the difference is <= 1 ulp per factor, 1e-15 relative on the strength.
-            const double inv_t = ddiv(1.0, tp_temp[tp]);
-            const double inv_z = ddiv(1.0, tp_isoz[(size_t)tp * V.niso + iso]);
+            const double temp = tp_temp[tp];
+            const double z = tp_isoz[(size_t)tp * V.niso + iso];
             const double pref = dmul(kSigCte, V.iso_ratio[iso]);
             const unsigned int s = V.g_start[g], e = V.g_start[g + 1];
             for (unsigned int ln = s; ln < e; ln++) {
                 const double w = V.l_wn[ln];
                 // SIGCTE*ratio*gf * exp(-EXPCTE*elow/T) * (1-exp(-EXPCTE*wn/T)) / Z   (:219-224)
-                const double pop = exp(dmul(dmul(-kExpCte, V.l_elow[ln]), inv_t));
-                const double ind = dsub(1.0, exp(dmul(dmul(-kExpCte, w), inv_t)));
-                const double kl = dmul(dmul(dmul(dmul(pref, V.l_gf[ln]), pop), ind), inv_z);
+                const double pop = exp(ddiv(dmul(-kExpCte, V.l_elow[ln]), temp));
+                const double ind = dsub(1.0, exp(ddiv(dmul(-kExpCte, w), temp)));
+                const double kl = ddiv(dmul(dmul(dmul(pref, V.l_gf[ln]), pop), ind), z);
                 k = (ln == s) ? kl : dadd(k, kl);  // :248,258 sequential co-add
                 best = fmax(best, kl);             // :225 maximum over single lines
             }

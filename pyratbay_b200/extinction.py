@@ -78,10 +78,16 @@ def compute_opacity(pyrat):
     if world == 1:
         extinction(pyrat, np.arange(n_units), grid=True, add=False)
     else:
-        mine = parallel.partition_units(n_units, rank, world)
+        # deal units to ranks by estimated cost (wide, high-pressure profiles cost more)
+        idx = np.arange(n_units)
+        cost = parallel.unit_costs(
+            pyrat.voigt, spec, pyrat.atm, lbl.iso_atm_index, lbl.iso_mass,
+            ex.temp[idx // ex.nlayers], ex.press[idx % ex.nlayers],
+            pyrat.atm.vmr[idx % ex.nlayers])
+        mine = parallel.partition_units(n_units, rank, world, cost)
         extinction(pyrat, mine, grid=True, add=False)
         flat = ex.etable.reshape(n_units, ex.nwave)
-        parallel.assemble_rows(flat, mine, device=pyrat.device)
+        parallel.assemble_rows(flat, mine, device=pyrat.device, cost=cost)
 
     if rank == 0:
         io.write_opacity(cs_file, ex.species, ex.temp, ex.press, ex.wn, ex.etable)

@@ -38,6 +38,28 @@ def partition_units(n_units, rank, world, cost=None):
     return np.where(owner == rank)[0]
 
 
+def unit_costs(voigt, spec, atm, iso_atm_index, iso_mass, temps, press, vmr):
+    """Relative cost of each (T,p) unit of a table for load balancing: the accumulate kernel's
+    work per line grows with the number of output samples a line reaches, i.e. with the Voigt
+    half-size selected by the unit's Lorentz width (constants of src_c/include/constants.h,
+    formulas of _extcoeff.c:138-183).  temps/press/vmr are per unit."""
+    kb, amu, c = 1.380658e-16, 1.66053886e-24, 2.99792458e10
+    temps = np.asarray(temps, np.double)
+    dens = np.asarray(vmr, np.double) * (np.asarray(press) * 1e6 / (1.380649e-16 * temps))[:, None]
+    imol = int(np.atleast_1d(iso_atm_index)[0])
+    mass = float(np.atleast_1d(iso_mass)[0])
+    diam = atm.mol_radius[imol] + atm.mol_radius
+    alor = (np.sqrt(2 * kb * temps / np.pi / amu) / c
+            * np.sum(dens * diam**2 * np.sqrt(1 / mass + 1 / atm.mol_mass), axis=1))
+    ilor = np.clip(np.searchsorted(voigt.lorentz, alor), 0, len(voigt.lorentz) - 1)
+    half = np.array([np.mean(voigt.size[i][voigt.size[i] > 0]) for i in ilor])
+    if voigt.cutoff > 0:
+        half = np.minimum(half, voigt.cutoff / spec.ownstep)
+    wnstep = spec.wn[1] - spec.wn[0] if len(spec.wn) > 1 else 1.0
+    footprint = 2.0 * half * spec.ownstep / wnstep       # output samples per line
+    return 15.0 + 8.0 * (1.0 + footprint / 32.0)          # warp-instruction model, DESIGN.md
+
+
 def assemble_rows(table, mine, device=None, cost=None):
     """All-gather the rows each rank computed into every rank's `table` [n_units, nwave].
 

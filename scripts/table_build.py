@@ -85,7 +85,11 @@ def main():
     temps = np.linspace(args.tmin, args.tmax, args.ntemp)
     z = workloads.partition(db, temps)                     # [ntemp, niso]
     n_units = args.ntemp * args.nlayers
-    mine = parallel.partition_units(n_units, rank, world)
+    all_idx = np.arange(n_units)
+    cost = parallel.unit_costs(voigt, spec, atm, iso_atm_index, db.iso_mass,
+                               temps[all_idx // args.nlayers], press[all_idx % args.nlayers],
+                               atm.vmr[all_idx % args.nlayers])
+    mine = parallel.partition_units(n_units, rank, world, cost)
     itemp, ilayer = mine // args.nlayers, mine % args.nlayers
     unit_t = temps[itemp]
     dens = atm.vmr[ilayer] * press[ilayer, None] * pc.bar / (pc.k * unit_t[:, None])
@@ -111,7 +115,7 @@ def main():
     if args.gather or args.out:
         t0 = time.time()
         if world > 1:
-            counts = [len(parallel.partition_units(n_units, r, world)) for r in range(world)]
+            counts = [len(parallel.partition_units(n_units, r, world, cost)) for r in range(world)]
             pad = max(counts)
             local = torch.zeros((pad, spec.nwave), dtype=torch.float64, device=d_out.device)
             local[:len(mine)] = d_out[:, 0]
@@ -120,7 +124,7 @@ def main():
             torch.cuda.synchronize()
             table = torch.empty((n_units, spec.nwave), dtype=torch.float64, device=d_out.device)
             for r in range(world):
-                idx = torch.from_numpy(parallel.partition_units(n_units, r, world)).to(d_out.device)
+                idx = torch.from_numpy(parallel.partition_units(n_units, r, world, cost)).to(d_out.device)
                 table[idx] = full[r * pad:r * pad + len(idx)]
         else:
             table = d_out[:, 0]
