@@ -171,6 +171,25 @@ int pb200_interp_ec_dev(int device, double *ext_dev, const double *etable_dev,
                         const double *density, int nspec, int ntemp, int nlayers,
                         int nwave, int lay1, int lay2, int per_mol, void *cuda_stream);
 
+/* Optical depth (next-tier row: the step after the extinction in Pyrat.run) ------------------
+ * Replaces lib._trapezoid.plane_parallel_optical_depth (src_c/_trapezoid.c:147-211) and the
+ * lib._trapezoid.optdepth loop of pyratbay/opacity/optic_depth.py:104-111 (transit geometry).
+ *   transit     0: plane-parallel (emission/eclipse paths), 1: grazing rays (transit)
+ *   depth       [nlayers, nwave] out (rows the reference leaves at zero are written as zero)
+ *   ideep       [nwave] int32 out: layer where each channel reached maxdepth (or the bottom)
+ *   extinction  [nlayers, nwave] (cm-1)
+ *   geometry    plane-parallel: intervals [nlayers-1] (cm); transit: [nlayers, nlayers]
+ *               zero-padded matrix whose row r holds raypath[r] (r - itop entries)
+ * The *_dev form takes depth/ideep/extinction as device pointers (extinction straight from
+ * pb200_extinction_batch_dev, no host round trip); geometry is always a host array. */
+int pb200_optical_depth(int device, int transit, double *depth, int32_t *ideep,
+                        const double *extinction, const double *geometry, double maxdepth,
+                        int itop, int ibottom, int nlayers, int nwave);
+int pb200_optical_depth_dev(int device, int transit, double *depth_dev, int32_t *ideep_dev,
+                            const double *extinction_dev, const double *geometry,
+                            double maxdepth, int itop, int ibottom, int nlayers, int nwave,
+                            void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,8 @@ def _lib():
         _LIB.orc_extinction.restype = ctypes.c_int
         _LIB.orc_interp_ec.restype = ctypes.c_int
         _LIB.orc_interp_ec_mol.restype = ctypes.c_int
+        _LIB.orc_plane_parallel_optical_depth.restype = ctypes.c_int
+        _LIB.orc_transit_optical_depth.restype = ctypes.c_int
     return _LIB
 
 
@@ -156,3 +158,31 @@ def interp_ec(extinction_out, etable, ttable, temperatures, density, lay1, lay2)
 def interp_ec_per_mol(extinction_out, etable, ttable, temperatures, density, lay1, lay2):
     return _interp(_lib().orc_interp_ec_mol, extinction_out, etable, ttable, temperatures,
                    density, lay1, lay2)
+
+
+def plane_parallel_optical_depth(depth, ideep, extinction, intervals, maxdepth, itop, ibottom):
+    """In place, same contract as _trapezoid.plane_parallel_optical_depth
+    (src_c/_trapezoid.c:147-211); ideep int32 [nwave]."""
+    assert depth.dtype == np.float64 and depth.flags.c_contiguous
+    assert ideep.dtype == np.int32 and ideep.flags.c_contiguous
+    ext, pext = _d(extinction)
+    dz, pdz = _d(intervals)
+    nlayers, nwave = depth.shape
+    _lib().orc_plane_parallel_optical_depth(
+        depth.ctypes.data_as(_dp), ideep.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), pext,
+        pdz, ctypes.c_double(maxdepth), ctypes.c_int(itop), ctypes.c_int(ibottom),
+        ctypes.c_int(nlayers), ctypes.c_int(nwave))
+
+
+def transit_optical_depth(depth, ideep, extinction, paths, maxdepth, itop, ibottom):
+    """Slant optical depth of optic_depth.py:104-111 + _trapezoid.optdepth; `paths` is the
+    [nlayers, nlayers] zero-padded matrix of ray paths (row r = raypath[r])."""
+    assert depth.dtype == np.float64 and depth.flags.c_contiguous
+    assert ideep.dtype == np.int32 and ideep.flags.c_contiguous
+    ext, pext = _d(extinction)
+    pa, ppa = _d(paths)
+    nlayers, nwave = depth.shape
+    _lib().orc_transit_optical_depth(
+        depth.ctypes.data_as(_dp), ideep.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), pext,
+        ppa, ctypes.c_double(maxdepth), ctypes.c_int(itop), ctypes.c_int(ibottom),
+        ctypes.c_int(nlayers), ctypes.c_int(nwave))

@@ -169,6 +169,26 @@ verb = 1
         ec_layer=ls.calc_extinction_coefficient(temp, dens1, layer=20))
     shutil.copy(ex.sampled_cs[0], os.path.join(HERE, "mock_opacity_file.npz"))
 
+    # 4b. Optical depth of the forward-model extinction (next-tier row) ---------------------------
+    from pyratbay.opacity.optic_depth import optical_depth as ref_optical_depth
+    radius = 7.0e9 + np.linspace(6.0e8, 0.0, atm.nlayers) ** 1.0     # cm, top to bottom
+    od = {"radius": radius, "ec": ec_all}
+    for name, kwargs in {
+            "emission": dict(rt_path="emission"),
+            "emission_max": dict(rt_path="emission", maxdepth=10.0, itop=3, ibottom=45),
+            "transit": dict(rt_path="transit"),
+            "transit_max": dict(rt_path="transit", maxdepth=10.0, itop=2, ibottom=48)}.items():
+        rp, depth, ideep, _, _ = ref_optical_depth(extinction=ec_all * 3e4, radius=radius,
+                                                    **kwargs)
+        od[name + "_depth"] = depth
+        od[name + "_ideep"] = np.asarray(ideep)
+    rp, depth, ideep, dclear, iclear = ref_optical_depth(
+        "transit", ec_all * 3e4, radius=radius, maxdepth=10.0,
+        extinction_cloudy=np.full_like(ec_all, 2e-9))
+    od.update(patchy_depth=depth, patchy_ideep=np.asarray(ideep), patchy_depth_clear=dclear,
+              patchy_ideep_clear=np.asarray(iclear))
+    np.savez_compressed(os.path.join(HERE, "mock_optical_depth.npz"), **od)
+
     # 5. Opacity table, constant-R (linterp) mode -------------------------------------------------
     write_cfg("opacity_R.cfg", base + "logfile = outputs/table_R.log\nresolution = 15000.0\n"
               "wnstep = 1.0\n")

@@ -404,3 +404,52 @@ def test_full_size_exact_linearity_and_isotope_additivity(full_size_engine):
     assert np.array_equal(doubled, 2.0 * base)
     # checksum of checksums: per-layer sums add up to the grand total
     assert abs(np.sum(np.sum(base, axis=-1)) / np.sum(base) - 1.0) < 1e-13
+
+
+# --------------------------------------------------------------- optical depth (next tier)
+@pytest.mark.parametrize("name", ["emission", "emission_max", "transit", "transit_max"])
+def test_optical_depth_matches_oracle_and_reference(name):
+    from pyratbay_b200.optic_depth import optical_depth, transit_path, _path_matrix
+    orc = helpers.oracle_module()
+    g = helpers.golden("mock_optical_depth.npz")
+    ec = np.ascontiguousarray(g["ec"] * 3e4)
+    nlayers, nwave = ec.shape
+    kw = {"emission": dict(rt_path="emission"),
+          "emission_max": dict(rt_path="emission", maxdepth=10.0, itop=3, ibottom=45),
+          "transit": dict(rt_path="transit"),
+          "transit_max": dict(rt_path="transit", maxdepth=10.0, itop=2, ibottom=48)}[name]
+    raypath, depth, ideep, dclear, iclear = optical_depth(extinction=ec, radius=g["radius"],
+                                                          **kw)
+    assert dclear is None and iclear is None
+    np.testing.assert_allclose(depth, g[name + "_depth"], rtol=1e-13, atol=0)
+    assert np.array_equal(ideep, g[name + "_ideep"])
+    # bit-exact against the strict-IEEE oracle
+    itop = kw.get("itop", 0)
+    ibottom = kw.get("ibottom", nlayers)
+    maxdepth = kw.get("maxdepth", np.inf)
+    want = np.zeros((nlayers, nwave))
+    wdeep = np.zeros(nwave, np.int32)
+    if kw["rt_path"] == "transit":
+        orc.transit_optical_depth(want, wdeep, ec, _path_matrix(transit_path(g["radius"], itop),
+                                                                 nlayers), maxdepth, itop, ibottom)
+    else:
+        orc.plane_parallel_optical_depth(want, wdeep, ec, -np.ediff1d(g["radius"]), maxdepth,
+                                         itop, ibottom)
+    assert np.array_equal(depth, want) and np.array_equal(ideep, wdeep)
+
+
+def test_optical_depth_patchy_and_errors():
+    from pyratbay_b200.optic_depth import optical_depth
+    g = helpers.golden("mock_optical_depth.npz")
+    ec = g["ec"] * 3e4
+    rp, depth, ideep, dclear, iclear = optical_depth(
+        "transit", ec, radius=g["radius"], maxdepth=10.0,
+        extinction_cloudy=np.full_like(ec, 2e-9))
+    np.testing.assert_allclose(depth, g["patchy_depth"], rtol=1e-13)
+    np.testing.assert_allclose(dclear, g["patchy_depth_clear"], rtol=1e-13)
+    assert np.array_equal(ideep, g["patchy_ideep"])
+    assert np.array_equal(iclear, g["patchy_ideep_clear"])
+    with pytest.raises(ValueError):
+        optical_depth("sideways", ec, radius=g["radius"])
+    with pytest.raises(ValueError):
+        optical_depth("transit", ec)

@@ -148,3 +148,33 @@ def test_oracle_interp_ec_matches_reference_line_sample():
     cs = np.zeros((1, nlayers, nwave))
     orc.interp_ec_per_mol(cs, table, temp, g["temperature"], np.ones((nlayers, 1)), 0, nlayers)
     np.testing.assert_allclose(cs, g["cs_per_mol"], rtol=1e-14)
+
+
+def _od_args(g, name):
+    kw = {"emission": dict(transit=False, maxdepth=np.inf, itop=0, ibottom=None),
+          "emission_max": dict(transit=False, maxdepth=10.0, itop=3, ibottom=45),
+          "transit": dict(transit=True, maxdepth=np.inf, itop=0, ibottom=None),
+          "transit_max": dict(transit=True, maxdepth=10.0, itop=2, ibottom=48)}[name]
+    return kw
+
+
+@pytest.mark.parametrize("name", ["emission", "emission_max", "transit", "transit_max"])
+def test_oracle_optical_depth_matches_reference(name):
+    """Optical depth (next-tier row) against the reference's optical_depth on the golden
+    forward-model extinction (tests/golden/make_golden.py section 4b)."""
+    from pyratbay_b200.optic_depth import transit_path, _path_matrix
+    g = helpers.golden("mock_optical_depth.npz")
+    ec = np.ascontiguousarray(g["ec"] * 3e4)
+    nlayers, nwave = ec.shape
+    kw = _od_args(g, name)
+    ibottom = nlayers if kw["ibottom"] is None else kw["ibottom"]
+    depth = np.zeros((nlayers, nwave))
+    ideep = np.zeros(nwave, np.int32)
+    if kw["transit"]:
+        paths = _path_matrix(transit_path(g["radius"], kw["itop"]), nlayers)
+        orc.transit_optical_depth(depth, ideep, ec, paths, kw["maxdepth"], kw["itop"], ibottom)
+    else:
+        orc.plane_parallel_optical_depth(depth, ideep, ec, -np.ediff1d(g["radius"]),
+                                         kw["maxdepth"], kw["itop"], ibottom)
+    np.testing.assert_allclose(depth, g[name + "_depth"], rtol=1e-13, atol=0)
+    assert np.array_equal(ideep, g[name + "_ideep"])
