@@ -150,6 +150,14 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(args):
+    """DRAM bytes of one accumulate launch from the committed ncu capture; only meaningful for
+    the default workload it was taken on."""
+    default = (args.nlines == 1_000_000 and args.nlayers == 81 and args.wl_low == 0.5
+               and args.wl_high == 5.0 and args.ptop == 1e-6 and args.pbottom == 100.0)
+    return 5.189576e9 + 18.259456e6 if default else None
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -275,13 +283,16 @@ def run_b200(args):
     fp64_tf, l2_gbs = device_ceilings(local_rank)
     roofline = {"bound": "hbm", "kernel": "accumulate_kernel<kTransposed>",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": ncu_traffic(args),
+                "traffic_source": "profiles/r01d_strengths_accumulate_v4.txt (ncu --set full, "
+                                  "dram__bytes_read+write of one launch; default workload only)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "algorithmic_bytes_groups_and_output": group_out_bytes,
                 "algorithmic_bytes_voigt_table_first_touch": float(table_bytes),
                 "launch_ms": acc_ms, "share_of_step": acc_ms / ms_per_step,
-                "note": "traffic (ncu dram bytes) is in profiles/; the kernel is issue/latency "
-                        "bound, see roofline_l2 / roofline_fp64 for the other ceilings"}
+                "note": "the kernel is issue/LSU bound (DESIGN.md section 5), see roofline_l2 / "
+                        "roofline_fp64 for the other ceilings"}
     roofline_l2 = {"bound": "l2", "achieved": 8.0 * gathered / (acc_ms * 1e-3) / 1e9,
                    "peak": l2_gbs, "unit": "GB/s",
                    "frac": 8.0 * gathered / (acc_ms * 1e-3) / 1e9 / l2_gbs,

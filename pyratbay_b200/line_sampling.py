@@ -68,7 +68,8 @@ class Line_Sample:
     """Line-by-line sampled opacities: cs_table [nspec, ntemp, nlayers, nwave]."""
 
     def __init__(self, cs_files, *, pressure=None, temperature=None, min_wl=None,
-                 max_wl=None, min_wn=None, max_wn=None, wl_thinning=1, device=0, log=None):
+                 max_wl=None, min_wn=None, max_wn=None, isotope_ratios=None, wl_thinning=1,
+                 device=0, log=None):
         self.name = 'line sampling'
         if isinstance(cs_files, str):
             cs_files = [cs_files]
@@ -95,8 +96,19 @@ class Line_Sample:
         self.wn = wn[mask][::wl_thinning]
         self.nwave = len(self.wn)
 
-        self.species = []
-        spec_indices, masks = [], []
+        # Isotopic parameters: lines "<file key> <label> <log10 ratio | fill_a_b>"
+        # (line_sampling.py:142-156)
+        iso_keys, iso_labels, iso_ratios = [], [], []
+        if isotope_ratios is not None:
+            for iso_data in isotope_ratios.strip().split('\n'):
+                ext_label, label, ratio = iso_data.split()
+                iso_keys.append(ext_label)
+                iso_labels.append('iso_' + label)
+                iso_ratios.append(ratio)
+
+        self.species, self.isotopes = [], []
+        iso_species, species_per_file = [], []
+        masks = []
         for cs_file in self.cs_files:
             species, _t, p, w = io.read_opacity(cs_file, extract='arrays')
             m = wn_mask(w, min_wn, max_wn)
@@ -107,12 +119,46 @@ class Line_Sample:
                     f"Wavenumber array of cross-section file '{cs_file}' "
                     "does not match with previous arrays")
             check_pressure_boundaries(self.press, p)
-            if species not in self.species:
+            iso = ''
+            for i, key in enumerate(iso_keys):
+                if key in cs_file and iso != '':
+                    raise ValueError(f'Multiple isotope labels match {repr(cs_file)}')
+                elif key in cs_file:
+                    iso = iso_labels[i]
+            species_per_file.append(species + iso)
+            if species + iso not in iso_species:
+                iso_species.append(species + iso)
                 self.species.append(species)
-            spec_indices.append(self.species.index(species))
+                self.isotopes.append(iso)
+        spec_indices = [iso_species.index(sp) for sp in species_per_file]
         self.species = np.array(self.species)
         self.nspec = len(self.species)
+
+        # Isotopic ratios: free parameters and fillers (line_sampling.py:198-229)
         self.iso_ratios = np.ones(self.nspec, float)
+        self.iso_fill = [None] * self.nspec
+        self._iso_free = []
+        self.pnames = []
+        pars = []
+        for i, iso in enumerate(self.isotopes):
+            if iso == '':
+                continue
+            ratio = iso_ratios[iso_labels.index(iso)]
+            if not ratio.startswith('fill_'):
+                self.iso_ratios[i] = 10.0**float(ratio)
+                self.pnames.append(iso)
+                self._iso_free.append(i)
+                pars.append(ratio)
+                continue
+            fillers = [f'iso_{filler}' for filler in ratio[5:].split('_')]
+            for filler in fillers:
+                if filler not in self.isotopes:
+                    raise ValueError('Invalid filler')
+            self.iso_fill[i] = [self.isotopes.index(filler) for filler in fillers]
+        self._update_iso_ratios()
+        self.pars = np.array(pars, float)
+        self.npars = len(self.pars)
+        self.texnames = list(self.pnames)
 
         self.cs_table = np.zeros((self.nspec, self.ntemp, self.nlayers, self.nwave))
         for i, cs_file in enumerate(self.cs_files):
@@ -121,6 +167,15 @@ class Line_Sample:
         self.tmin = np.amin(self.temp)
         self.tmax = np.amax(self.temp)
         self._dev_table = None
+
+    def _update_iso_ratios(self, pars=None):
+        """Update the isotopic ratios, keeping the fillers complementary
+        (line_sampling.py:278-293)."""
+        if pars is not None:
+            self.iso_ratios[self._iso_free] = 10.0**np.array(pars)
+        for i, fillers in enumerate(self.iso_fill):
+            if fillers is not None:
+                self.iso_ratios[i] = 1.0 - np.sum(self.iso_ratios[fillers])
 
     def get_wl(self, units='um'):
         return 1.0 / (self.wn * pc.u(units))
@@ -157,13 +212,18 @@ class Line_Sample:
             out = out[:, layer] if per_mol else out[layer]
         return out
 
-    def calc_cross_section(self, temperature, layer=None, per_mol=False):
+    def calc_cross_section(self, temperature, layer=None, per_mol=False, pars=None):
         """Cross sections (cm2 molec-1) at the given layer temperatures
         (line_sampling.py:317-391)."""
+        if pars is not None:
+            self._update_iso_ratios(pars)
         density = np.ones((self.nlayers, self.nspec)) * self.iso_ratios
         return self._interp(np.asarray(temperature, np.double), density, layer, per_mol)
 
-    def calc_extinction_coefficient(self, temperature, density, layer=None, per_mol=False):
+    def calc_extinction_coefficient(self, temperature, density, layer=None, per_mol=False,
+                                    pars=None):
         """Extinction coefficient (cm-1) (line_sampling.py:394-463); density [nlayers, nspec]."""
+        if pars is not None:
+            self._update_iso_ratios(pars)
         density = np.asarray(density, np.double) * self.iso_ratios
         return self._interp(np.asarray(temperature, np.double), density, layer, per_mol)

@@ -168,6 +168,18 @@ verb = 1
         ec=ls.calc_extinction_coefficient(temp, dens1),
         ec_layer=ls.calc_extinction_coefficient(temp, dens1, layer=20))
     shutil.copy(ex.sampled_cs[0], os.path.join(HERE, "mock_opacity_file.npz"))
+    # the same table read twice as two isotopologues with a free and a filler ratio
+    iso_a, iso_b = os.path.join(run, "cs_H2O_161.npz"), os.path.join(run, "cs_H2O_181.npz")
+    shutil.copy(ex.sampled_cs[0], iso_a)
+    shutil.copy(ex.sampled_cs[0], iso_b)
+    ls2 = op.Line_Sample([iso_a, iso_b], isotope_ratios="161 main fill_heavy\n181 heavy -2.5")
+    dens2 = np.tile(dens1, (1, 2))
+    np.savez_compressed(
+        os.path.join(HERE, "mock_line_sample_iso.npz"), iso_ratios=ls2.iso_ratios,
+        pnames=np.array(ls2.pnames), pars=ls2.pars, species=ls2.species,
+        ec=ls2.calc_extinction_coefficient(temp, dens2),
+        ec_pars=ls2.calc_extinction_coefficient(temp, dens2, pars=[-3.0]),
+        iso_ratios_after=ls2.iso_ratios, cs_per_mol=ls2.calc_cross_section(temp, per_mol=True))
 
     # 4b. Optical depth of the forward-model extinction (next-tier row) ---------------------------
     from pyratbay.opacity.optic_depth import optical_depth as ref_optical_depth

@@ -453,3 +453,27 @@ def test_optical_depth_patchy_and_errors():
         optical_depth("sideways", ec, radius=g["radius"])
     with pytest.raises(ValueError):
         optical_depth("transit", ec)
+
+
+def test_line_sample_isotope_ratios_match_reference(tmp_path):
+    """Two tables labelled as isotopologues with one free and one filler ratio
+    (line_sampling.py:142-229), extinction before and after updating the parameter."""
+    import shutil
+    import pyratbay_b200 as pb
+    g = helpers.golden("mock_line_sample_iso.npz")
+    g1 = helpers.golden("mock_line_sample.npz")
+    src = os.path.join(helpers.GOLDEN, "mock_opacity_file.npz")
+    a, b = str(tmp_path / "cs_H2O_161.npz"), str(tmp_path / "cs_H2O_181.npz")
+    shutil.copy(src, a)
+    shutil.copy(src, b)
+    ls = pb.Line_Sample([a, b], isotope_ratios="161 main fill_heavy\n181 heavy -2.5")
+    assert list(ls.species) == list(g["species"]) and list(ls.pnames) == list(g["pnames"])
+    assert np.array_equal(ls.pars, g["pars"])
+    temp = g1["temperature"]
+    dens = np.tile(g1["density"], (1, 2))
+    np.testing.assert_allclose(ls.calc_extinction_coefficient(temp, dens), g["ec"], rtol=1e-14)
+    np.testing.assert_allclose(ls.calc_extinction_coefficient(temp, dens, pars=[-3.0]),
+                               g["ec_pars"], rtol=1e-14)
+    np.testing.assert_allclose(ls.iso_ratios, g["iso_ratios_after"], rtol=0, atol=0)
+    np.testing.assert_allclose(ls.calc_cross_section(temp, per_mol=True), g["cs_per_mol"],
+                               rtol=1e-14)
