@@ -148,7 +148,8 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
                   const IsoUnit *__restrict__ iso_units, const int *__restrict__ iso_row,
                   const double *__restrict__ ksum,
                   const unsigned long long *__restrict__ kmax, int nrows, double ethresh,
-                  double cutoff, double *__restrict__ out) {
+                  double cutoff, double *__restrict__ out, int ksplit,
+                  double *__restrict__ partial) {
     extern __shared__ double s_doppler[];  // [ndop]
     // One staged group per lane: {k, byte address of its sample for coordinate 0} and
     // {first coordinate, number of coordinates}.
@@ -161,7 +162,12 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const UnitParams U = units[blockIdx.y];
     const int row = blockIdx.z;
-    const int m = blockIdx.x * kTileOutputs + threadIdx.x;
+    // ksplit CTAs share one tile: CTA `split` takes every ksplit-th chunk of each warp's
+    // candidate list and writes a partial sum (reduced by reduce_partials_kernel).  With
+    // tiles*ksplit close to the number of resident CTAs, all CTAs in flight work on ONE unit,
+    // so that unit's Voigt profiles stay L2-resident while they are gathered.
+    const int tile = blockIdx.x / ksplit, split = blockIdx.x - tile * ksplit;
+    const int m = tile * kTileOutputs + threadIdx.x;
     const bool in_grid = m < V.nwave;
     const double *__restrict__ table = (MODE == kTransposed) ? V.tprofile : V.profile;
     const int mult = (MODE == kTransposed) ? 1 : U.ofactor;            // address stride per x
@@ -219,19 +225,20 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
             // that their latency overlaps the slot loop
             double nx_w = 0.0, nx_k = 0.0;
             int nx_iown = 0;
-            if (glo + lane < ghi) {
-                nx_w = V.g_wn[glo + lane];
-                nx_iown = V.g_iown[glo + lane];
-                nx_k = ks[glo + lane];
+            const int cstep = 32 * ksplit;
+            if (glo + 32 * split + lane < ghi) {
+                nx_w = V.g_wn[glo + 32 * split + lane];
+                nx_iown = V.g_iown[glo + 32 * split + lane];
+                nx_k = ks[glo + 32 * split + lane];
             }
-            for (int c = glo; c < ghi; c += 32) {
+            for (int c = glo + 32 * split; c < ghi; c += cstep) {
                 const int g = c + lane;
                 const double cur_w = nx_w, cur_k = nx_k;
                 const int cur_iown = nx_iown;
-                if (g + 32 < ghi) {
-                    nx_w = V.g_wn[g + 32];
-                    nx_iown = V.g_iown[g + 32];
-                    nx_k = ks[g + 32];
+                if (g + cstep < ghi) {
+                    nx_w = V.g_wn[g + cstep];
+                    nx_iown = V.g_iown[g + cstep];
+                    nx_k = ks[g + cstep];
                 }
                 Prep p;
                 p.k = 0.0; p.base = 0; p.lo = 0; p.hi = 0;
@@ -266,7 +273,9 @@ PB200_PRAGMA_UNROLL
         }
     }
     if (in_grid) {
-        double *dst = out + ((size_t)U.out_index * nrows + row) * (size_t)V.nwave;
+        double *dst = ksplit > 1
+            ? partial + (((size_t)blockIdx.y * nrows + row) * ksplit + split) * (size_t)V.nwave
+            : out + ((size_t)U.out_index * nrows + row) * (size_t)V.nwave;
         if (MODE == kLinterp) {
             const double wlo = dadd(V.wn0, dmul(U.dwnstep, (double)x0));
             dst[m] = (acc0 * (wlo + U.dwnstep - wn_i) + acc1 * (wn_i - wlo)) / U.dwnstep;
@@ -274,6 +283,19 @@ PB200_PRAGMA_UNROLL
             dst[m] = acc0;  // 0 beyond mcount
         }
     }
+}
+
+// Sum the ksplit partial spectra of every (unit, row) in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const UnitParams *__restrict__ units, const double *__restrict__ partial,
+                       int nrows, int ksplit, int nwave, double *__restrict__ out) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nwave) return;
+    const int row = blockIdx.z;
+    const double *src = partial + (((size_t)blockIdx.y * nrows + row) * ksplit) * (size_t)nwave + m;
+    double acc = src[0];
+    for (int s = 1; s < ksplit; s++) acc += src[(size_t)s * nwave];
+    out[((size_t)units[blockIdx.y].out_index * nrows + row) * (size_t)nwave + m] = acc;
 }
 
 // One-time re-layout of the Voigt table: block of profile p is T[r][q] = P[q*stride + r].
@@ -415,21 +437,28 @@ int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double
 int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
                       const UnitParams *units, const IsoUnit *iso_units, const int *iso_row,
                       const double *ksum, const unsigned long long *kmax, int nrows,
-                      double ethresh, double cutoff, int mode, double *out) {
+                      double ethresh, double cutoff, int mode, double *out, int ksplit,
+                      double *partial) {
     if (nunits == 0 || V.nwave == 0) return 0;
-    dim3 grid((unsigned)((V.nwave + kTileOutputs - 1) / kTileOutputs), (unsigned)nunits,
-              (unsigned)nrows);
+    if (ksplit < 1 || !partial) ksplit = 1;
+    const int ntiles = (V.nwave + kTileOutputs - 1) / kTileOutputs;
+    dim3 grid((unsigned)(ntiles * ksplit), (unsigned)nunits, (unsigned)nrows);
     const size_t smem = sizeof(double) * V.ndop;
     if (mode == kLinterp)
         accumulate_kernel<kLinterp><<<grid, 256, smem, st>>>(
-            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out);
+            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
     else if (mode == kTransposed)
         accumulate_kernel<kTransposed><<<grid, 256, smem, st>>>(
-            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out);
+            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
     else
         accumulate_kernel<kStrided><<<grid, 256, smem, st>>>(
-            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out);
+            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
     PB_CUDA(cudaGetLastError());
+    if (ksplit > 1) {
+        dim3 rgrid((unsigned)((V.nwave + 255) / 256), (unsigned)nunits, (unsigned)nrows);
+        reduce_partials_kernel<<<rgrid, 256, 0, st>>>(units, partial, nrows, ksplit, V.nwave, out);
+        PB_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 
