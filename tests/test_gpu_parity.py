@@ -477,3 +477,64 @@ def test_line_sample_isotope_ratios_match_reference(tmp_path):
     np.testing.assert_allclose(ls.iso_ratios, g["iso_ratios_after"], rtol=0, atol=0)
     np.testing.assert_allclose(ls.calc_cross_section(temp, per_mol=True), g["cs_per_mol"],
                                rtol=1e-14)
+
+
+def test_two_species_through_line_by_line_api(tmp_path):
+    """Two single-database TLI files (the reference offsets isotope ids per file,
+    line_by_line.py:119-121): co-added extinction, per-species get_ec and skip_mol, through
+    the Pyrat-shaped API, against the oracle fed with the same concatenated arrays."""
+    import pyratbay_b200 as pb
+    from pyratbay_b200 import tli as ptli
+    orc = helpers.oracle_module()
+    temp, z = ptli.h2o_partition_table()
+    db_a = ptli.Database("Synthetic H2O", "H2O", temp, ["116", "118"], [18.01056, 20.01481],
+                         [0.9973, 0.0020], z[:2])
+    db_b = ptli.Database("Synthetic CO", "CO", temp, ["26", "36", "28"],
+                         [27.9949, 28.9983, 29.9992], [0.9865, 0.0111, 0.0020], z[1:4] * 0.31)
+    files = []
+    for k, (db, n) in enumerate([(db_a, 6000), (db_b, 4000)]):
+        fr = tuple(np.array([0.8, 0.2]) if db.niso == 2 else np.array([0.7, 0.2, 0.1]))
+        wn, elow, gf, iso, counts = ptli.synthetic_lines(n, 4990.0, 5215.0, fractions=fr,
+                                                         seed=10 + k)
+        path = str(tmp_path / f"syn_{k}.tli")
+        ptli.write_tli(path, [db], [{"wn": wn, "elow": elow, "gf": gf, "iso_id": iso,
+                                     "n_lines_iso": counts}], 4990.0, 5215.0)
+        files.append(path)
+    a = helpers.golden("mock_atmosphere.npz")
+    nlayers = 7
+    from pyratbay_b200 import atmosphere as pa
+    atm = pa.Atmosphere(pa.pressure(1e-5, 50.0, nlayers), np.linspace(600.0, 2400.0, nlayers),
+                        np.tile(a["vmr"][0], (nlayers, 1)), [str(s) for s in a["species"]])
+    inputs = dict(tlifile=files, wnlow=5000.0, wnhigh=5200.0, wnstep=1.0, wnosamp=720,
+                  voigt_extent=50.0, voigt_nlor=30, voigt_ndop=12, tmin=300.0, tmax=3000.0,
+                  verb=0)
+    pyrat = pb.Pyrat(inputs, atm=atm)
+    lbl, spec, voigt = pyrat.lbl, pyrat.spec, pyrat.voigt
+    assert list(lbl.species) == ["CO", "H2O"] and lbl.nspec == 2 and lbl.niso == 5
+    assert list(lbl.iso_mol_index) == [1, 1, 0, 0, 0]
+    profile = voigt.profile
+    isoz = lbl.partition(atm.temp).T
+
+    def oracle(layer, add, iext):
+        ext = np.zeros((lbl.nspec, spec.nwave))
+        orc.extinction(ext, profile, voigt.size, voigt.index, voigt.lorentz, voigt.doppler,
+                       spec.wn, spec.own, spec.odivisors, atm.d[layer], atm.mol_radius,
+                       atm.mol_mass, lbl.iso_atm_index, lbl.iso_mass, lbl.iso_ratio,
+                       isoz[layer], iext, lbl.wn, lbl.elow, lbl.gf, lbl.isoid, voigt.cutoff,
+                       lbl.ethresh, atm.temp[layer], 0, int(add), 0)
+        return ext
+
+    ec = pyrat.calc_lbl_extinction()
+    for layer in range(nlayers):
+        assert _peak_err(ec[layer], oracle(layer, True, lbl.iso_mol_index)[0]) < TOL_PEAK
+    per_species, label = pyrat.get_ec(3)
+    want = oracle(3, False, lbl.iso_mol_index) * atm.d[3, lbl.mol_index][:, None]
+    assert label == ["CO", "H2O"] and _peak_err(per_species, want) < TOL_PEAK
+    skipped = np.copy(pyrat.calc_lbl_extinction(skip_mol=["CO"]))
+    iext = np.where(lbl.iso_mol_index == 0, -1, lbl.iso_mol_index)
+    for layer in (0, 6):
+        assert _peak_err(skipped[layer], oracle(layer, True, iext)[0]) < TOL_PEAK
+    with pytest.raises(ValueError):   # tables are single-species (pyrat/extinction.py:57-62)
+        pyrat.ex.tmin, pyrat.ex.tmax, pyrat.ex.tstep = 300.0, 3000.0, 300.0
+        pyrat.ex.sampled_cs = [str(tmp_path / "t.npz")]
+        pyrat.compute_opacity()
