@@ -53,10 +53,12 @@ def parse_args():
 def workload_config(args):
     return {
         "workload": (f"synthetic {args.nlines:.0e}-line H2O TLI, {args.nlayers}-layer "
-                     "atmosphere 1e-6..100 bar, 0.5-5 um forward-model extinction (add=1), "
+                     f"atmosphere {args.ptop:g}..{args.pbottom:g} bar, {args.wl_low:g}-"
+                     f"{args.wl_high:g} um forward-model extinction (add=1), "
                      "wnstep=1 cm-1, wnosamp=2160, voigt extent 300 HWHM, cutoff 25 cm-1, "
                      "ethresh 1e-30"),
         "nlines": args.nlines, "nlayers": args.nlayers,
+        "wl_um": [args.wl_low, args.wl_high], "p_bar": [args.ptop, args.pbottom],
         "units_per_step_per_gpu": args.nlayers,
         "l2": "no explicit flush: per-step working set (ksum 8 B x groups x layers + Voigt "
               "table 1.2 GB + output) exceeds the 126 MB L2",
