@@ -275,3 +275,23 @@ def test_table_assembly_across_two_ranks_gloo(tmp_path):
     full = np.arange(23 * 17, dtype=np.double).reshape(23, 17) ** 1.5
     for r in range(2):
         assert np.array_equal(np.load(tmp_path / f"table_{r}.npy"), full)
+
+
+def test_unit_costs_balance_table_partition():
+    """Cost model used to deal (T,p) units to ranks: grows with pressure (wider profiles) and
+    gives a far better balance than round-robin would on cost."""
+    from pyratbay_b200 import parallel
+    c = helpers.mock_case(with_profile=False)
+    ntemp, nlayers = 10, c.atm.nlayers
+    temps = np.repeat(np.linspace(300, 3000, ntemp), nlayers)
+    press = np.tile(c.atm.press, ntemp)
+    vmr = np.tile(c.atm.vmr, (ntemp, 1))
+    cost = parallel.unit_costs(c.voigt, c.spec, c.atm, c.iso_atm_index, c.iso_mass, temps,
+                               press, vmr)
+    assert cost.shape == (ntemp * nlayers,) and np.all(cost > 0)
+    per_layer = cost[:nlayers]
+    assert per_layer[-1] > per_layer[0]          # 100 bar costs more than 1e-6 bar
+    parts = [parallel.partition_units(len(cost), r, 8, cost) for r in range(8)]
+    assert sorted(np.concatenate(parts)) == list(range(len(cost)))
+    loads = np.array([cost[p].sum() for p in parts])
+    assert loads.max() / loads.min() < 1.03
