@@ -15,6 +15,7 @@
 
 #include "../../include/pb200_lbl.h"
 #include "lbl_kernels.cuh"
+#include "preprocess.cuh"
 #include "voigt.cuh"
 
 namespace pb200 {
@@ -450,18 +451,81 @@ int pb200_engine_set_lines(pb200_engine *e, int64_t nlines, const double *wn,
 
     // Isotopes must come in contiguous blocks, ascending wavenumber inside (TLI layout).
     std::vector<char> seen(niso, 0);
+    std::vector<long long> block_start;
+    std::vector<int> block_iso;
+    std::vector<unsigned short> iso16((size_t)nlines);
     for (int64_t ln = 0; ln < nlines; ln++) {
         const int64_t i = iso_id[ln];
         if (i < 0 || i >= niso)
             return fail(PB200_EINVAL, "pb200_engine_set_lines: isotope id out of range");
+        iso16[ln] = (unsigned short)i;
         if (ln == 0 || iso_id[ln - 1] != i) {
             if (seen[i])
                 return fail(PB200_EINVAL, "pb200_engine_set_lines: an isotope appears in more "
                                           "than one block; lines must be grouped by isotope");
             seen[i] = 1;
+            block_start.push_back(ln);
+            block_iso.push_back((int)i);
         } else if (wn[ln] < wn[ln - 1]) {
             return fail(PB200_EINVAL, "pb200_engine_set_lines: wavenumbers must ascend within "
                                       "each isotope block");
+        }
+    }
+
+    // Coarse per-isotope index geometry over the fine grid.
+    const int binw_all = (int)std::max<int64_t>(64, onwn >> 16);
+    const int nbins_all = (int)((onwn + binw_all - 1) / binw_all);
+
+    // Device path (default for large lists; PB200_SETLINES=host|device overrides): the
+    // grouping, compaction and coarse index are built on the GPU (preprocess.cu).
+    {
+        const char *mode = std::getenv("PB200_SETLINES");
+        const bool on_device = mode ? std::strcmp(mode, "device") == 0 : nlines >= 200000;
+        if (on_device && nlines > 0) {
+            GroupInput gi;
+            gi.nlines = nlines; gi.wn = wn; gi.elow = elow; gi.gf = gf; gi.iso16 = iso16.data();
+            gi.own = own; gi.onwn = onwn; gi.niso = niso;
+            gi.nblocks = (int)block_start.size();
+            gi.block_start = block_start.data(); gi.block_iso = block_iso.data();
+            gi.nbins = nbins_all; gi.binw = binw_all;
+            GroupOutput go;
+            struct Ctx { pb200_engine *e; GroupOutput *go; int niso, nbins; } ctx{e, &go, niso, nbins_all};
+            go.ctx = &ctx;
+            go.alloc = [](void *c, long long n_inwin, long long ngroups) -> int {
+                Ctx *x = (Ctx *)c;
+                pb200_engine *en = x->e;
+                int r = en->d_lwn.alloc((size_t)std::max<long long>(n_inwin, 1));
+                if (!r) r = en->d_lelow.alloc((size_t)std::max<long long>(n_inwin, 1));
+                if (!r) r = en->d_lgf.alloc((size_t)std::max<long long>(n_inwin, 1));
+                if (!r) r = en->d_gwn.alloc((size_t)std::max<long long>(ngroups, 1));
+                if (!r) r = en->d_giown.alloc((size_t)std::max<long long>(ngroups, 1));
+                if (!r) r = en->d_gstart.alloc((size_t)ngroups + 1);
+                if (!r) r = en->d_giso.alloc((size_t)std::max<long long>(ngroups, 1));
+                if (!r) r = en->d_gbin.alloc((size_t)x->niso * (x->nbins + 1));
+                if (r) return r;
+                x->go->l_wn = en->d_lwn.p; x->go->l_elow = en->d_lelow.p; x->go->l_gf = en->d_lgf.p;
+                x->go->g_wn = en->d_gwn.p; x->go->g_iown = en->d_giown.p;
+                x->go->g_start = en->d_gstart.p; x->go->g_iso = en->d_giso.p;
+                x->go->gbin = en->d_gbin.p;
+                return 0;
+            };
+            e->has_lines = false;
+            int rc = device_group_lines(e->stream, gi, &go);
+            if (rc) return rc;
+            e->launches += 9;
+            e->iso_nadd.assign(niso, 0);
+            int64_t nadd_dev = 0;
+            for (int i = 0; i < niso; i++) {
+                e->iso_nadd[i] = go.iso_nadd.empty() ? 0 : go.iso_nadd[i];
+                nadd_dev += e->iso_nadd[i];
+            }
+            e->n_inwin = go.n_inwin;
+            e->ngroups = go.ngroups;
+            e->nadd = nadd_dev;
+            e->nbins = nbins_all;
+            e->binw = binw_all;
+            e->has_lines = true;
+            return 0;
         }
     }
 
@@ -505,8 +569,7 @@ int pb200_engine_set_lines(pb200_engine *e, int64_t nlines, const double *wn,
     const int64_t ngroups = (int64_t)g_wn.size();
 
     // Coarse per-isotope index over the fine grid.
-    int binw = (int)std::max<int64_t>(64, onwn >> 16);
-    int nbins = (int)((onwn + binw - 1) / binw);
+    const int binw = binw_all, nbins = nbins_all;
     std::vector<int> gbin((size_t)niso * (nbins + 1), 0);
     {
         int64_t g = 0;

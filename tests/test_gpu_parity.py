@@ -538,3 +538,59 @@ def test_two_species_through_line_by_line_api(tmp_path):
         pyrat.ex.tmin, pyrat.ex.tmax, pyrat.ex.tstep = 300.0, 3000.0, 300.0
         pyrat.ex.sampled_cs = [str(tmp_path / "t.npz")]
         pyrat.compute_opacity()
+
+
+@pytest.mark.parametrize("kwargs", [
+    dict(nlines=20000),
+    dict(nlines=200000, wnosamp=120),                       # dense: long co-add chains
+    dict(nlines=60000, wnstep=0.25, wnosamp=360, wnlow=9000.0, wnhigh=9060.0),
+])
+def test_device_line_preprocessing_matches_host(kwargs, monkeypatch):
+    """pb200_engine_set_lines on the device (segment-parallel co-add walk, csrc/preprocess.cu)
+    against the sequential host walk: identical groups, hence bit-identical extinction."""
+    case = helpers.synthetic_case(**kwargs)
+    temps, dens = case.atm.temp, case.atm.d
+    isoz = helpers.partition(case, temps).T
+    results = {}
+    for mode in ("host", "device"):
+        monkeypatch.setenv("PB200_SETLINES", mode)
+        eng = _engine_for(case, profile="host")
+        results[mode] = (eng.line_stats(),
+                         eng.extinction_batch(temps, dens, isoz, case.iso_mol_index, 1,
+                                              case.ethresh, 1, 0, counters=True))
+        eng.close()
+    assert results["host"][0] == results["device"][0]
+    assert results["host"][0]["nadd"] > 0
+    assert np.array_equal(results["host"][1][0], results["device"][1][0])
+    assert np.array_equal(results["host"][1][1], results["device"][1][1])
+
+
+def test_device_line_preprocessing_edge_cases(monkeypatch):
+    """Window edges, duplicates, blocks entirely outside the window, a single line."""
+    case = helpers.synthetic_case(nlines=2000)
+    own, step = case.spec.own, case.spec.ownstep
+    temps, dens = case.atm.temp[:2], case.atm.d[:2]
+    isoz = helpers.partition(case, temps).T
+    blocks = [
+        # isotope 0: below the window, on its edge, duplicates and near-duplicates
+        np.array([own[0] - 3.0, own[0] - 1e-9, own[0], own[5], own[5], own[5] + 0.4 * step,
+                  own[5] + 0.9 * step, own[5] + 1.1 * step, own[9] + 0.5 * step, own[-1],
+                  own[-1] + 1e-9, own[-1] + 2.0]),
+        np.array([own[0] - 9.0, own[0] - 8.0]),                    # isotope 1: all below
+        np.array([own[100] + 0.49 * step]),                        # isotope 2: one line
+        np.array([own[-1] + 1.0, own[-1] + 2.0, own[-1] + 2.0]),   # isotope 3: all above
+    ]
+    lw = np.concatenate(blocks)
+    iso = np.concatenate([np.full(len(b), i) for i, b in enumerate(blocks)])
+    elow, gf = np.full(len(lw), 100.0), np.full(len(lw), 1e-6)
+    out = {}
+    for mode in ("host", "device"):
+        monkeypatch.setenv("PB200_SETLINES", mode)
+        eng = _engine_for(helpers.Case(**{**case.__dict__, "lwn": lw, "elow": elow, "gf": gf,
+                                          "isoid": iso}), profile="host")
+        out[mode] = (eng.line_stats(), eng.extinction_batch(
+            temps, dens, isoz, case.iso_mol_index, 1, 1e-30, 1, 0, counters=True))
+        eng.close()
+    assert out["host"][0] == out["device"][0]
+    assert np.array_equal(out["host"][1][0], out["device"][1][0])
+    assert np.array_equal(out["host"][1][1], out["device"][1][1])
