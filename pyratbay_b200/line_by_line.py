@@ -117,3 +117,41 @@ class Line_By_Line:
         ex.extinction(self.pyrat, np.arange(self.nlayers), grid=False, add=True,
                       skip_mol=skip_mol)
         return self.ec
+
+    def __str__(self):
+        """Same text as the reference's Line_By_Line.__str__ (line_by_line.py:251-295)."""
+        from .tools import Formatted_Write
+        fw = Formatted_Write()
+        fw.write('Line-transition information:')
+        fw.write('Input TLI files (tlifile): {}', self.tlifile)
+        fw.write('Number of databases (ndb): {:d}', self.ndb)
+        for db in self.db:
+            fw.write('\n' + str(db))
+        fw.write(
+            '\nTotal number of line transitions (ntransitions): {:,d}\n'
+            'Minimum and maximum temperatures (tmin, tmax): [{:.1f}, {:.1f}] K',
+            self.ntransitions, self.tmin, self.tmax)
+        fw.write('Line-transition isotope IDs (isoid):\n    {}', self.isoid, edge=7)
+        fw.write('Line-transition wavenumbers (wn, cm-1):\n    {}', self.wn,
+                 fmt={'float': '{:.3f}'.format}, edge=3)
+        fw.write('Line-transition lower-state energy (elow, cm-1):\n    {}', self.elow,
+                 fmt={'float': '{: .3e}'.format}, edge=3)
+        fw.write('Line-transition gf (gf, cm-1):\n    {}', self.gf,
+                 fmt={'float': '{: .3e}'.format}, edge=3)
+        fw.write('Line-transition strength threshold (ethresh): {:.2e}', self.ethresh)
+        fw.write('Isotopes information:')
+        fw.write('Number of isotopes (niso): {:d}', self.niso)
+        fw.write(
+            '\nIsotope  Molecule      Mass    Isotopic   Database'
+            '\n            index     g/mol       ratio'
+            '\n (name)    (imol)    (mass)     (ratio)')
+        iso_index = db_index = 0
+        for i in range(self.niso):
+            fw.write('{:>7s}  {:8d}  {:8.4f}   {:.3e}   {}', self.iso_name[i],
+                     self.iso_atm_index[i], self.iso_mass[i], self.iso_ratio[i],
+                     self.db[db_index].name)
+            iso_index += 1
+            if iso_index == self.db[db_index].niso:
+                db_index += 1
+                iso_index = 0
+        return fw.text

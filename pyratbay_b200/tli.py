@@ -30,10 +30,18 @@ class Database:
         self.iso_pf = np.asarray(iso_pf, np.double).reshape(self.niso, self.ntemp)
 
     def __str__(self):
-        return (f"Database name (name): {self.name}\n"
-                f"Species name (molname):  {self.molname}\n"
-                f"Number of isotopes (niso): {self.niso}\n"
-                f"Number of temperature samples (ntemp): {self.ntemp}")
+        """Same text as the reference's Database.__str__ (line_by_line.py:58-68)."""
+        from .tools import Formatted_Write
+        fw = Formatted_Write()
+        fw.write('Database name (name): {:s}', self.name)
+        fw.write('Species name (molname):  {:s}', self.molname)
+        fw.write('Number of isotopes (niso): {:d}', self.niso)
+        fw.write('Number of temperature samples (ntemp): {:d}', self.ntemp)
+        fw.write('Temperature (temp, K):\n    {}', self.temp, prec=3, edge=3)
+        fw.write('Partition function for each isotope (z):')
+        for z in self.iso_pf:
+            fw.write('    {}', z, fmt={'float': '{: .3e}'.format}, edge=3)
+        return fw.text
 
 
 def _read(fmt, f):

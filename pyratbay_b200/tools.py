@@ -2,8 +2,12 @@
 subset of `[pyrat]` configuration keys that drive the opacity path."""
 import configparser
 import os
+import string
 import sys
+import textwrap
 from types import SimpleNamespace
+
+import numpy as np
 
 from . import constants as pc
 
@@ -48,6 +52,42 @@ class Log:
         if self.file is not None:
             self.file.close()
             self.file = None
+
+
+class Formatted_Write(string.Formatter):
+    """Accumulate formatted, wrapped text (same contract as the reference's
+    tools.Formatted_Write, tools/tools.py:736-829): `None` prints as 'None' under any format
+    spec, NumPy arrays are rendered under temporary printoptions, lines wrap at 80 columns."""
+
+    def __init__(self, indent=0, si=4, fmt=None, edge=None, lw=80, prec=None):
+        self.text = ''
+        self.indent = indent
+        self.si = si
+        self.fmt, self.edge, self.lw, self.prec = fmt, edge, lw, prec
+
+    def format_field(self, value, spec):
+        if value is None:
+            return 'None'
+        return super().format_field(value, spec)
+
+    def write(self, text, *format, **numpy_fmt):
+        opts = {'fmt': self.fmt, 'edge': self.edge, 'lw': self.lw, 'prec': self.prec}
+        opts.update(numpy_fmt)
+        printopts = {
+            'formatter': opts['fmt'],
+            'edgeitems': opts['edge'],
+            'threshold': None if opts['edge'] is None else 2 * opts['edge'],
+            'linewidth': opts['lw'],
+            'precision': opts['prec'],
+        }
+        with np.printoptions(**printopts):
+            text = super().format(text, *format)
+        first = ' ' * self.indent
+        rest = first if self.si is None else ' ' * self.si
+        for line in text.splitlines():
+            self.text += textwrap.fill(line, break_long_words=False, initial_indent=first,
+                                       subsequent_indent=rest, width=80)
+            self.text += '\n'
 
 
 def _value_units(text, default_units=None):

@@ -101,21 +101,27 @@ class Voigt:
         return self._profile
 
     def __str__(self):
-        with np.printoptions(formatter={'float': '{:.3e}'.format}, edgeitems=3,
-                             threshold=6):
-            text = (
-                'Voigt-profile information:\n'
-                f'\nNumber of Doppler-width samples (ndop): {self.ndop:d}\n'
-                f'Number of Lorentz-width samples (nlor): {self.nlor:d}\n'
-                f'Doppler HWHM (doppler, cm-1):\n    {self.doppler}\n'
-                f'Lorentz HWMH (lorentz, cm-1):\n    {self.lorentz}\n'
-                f'Doppler--Lorentz ratio threshold (dlratio): {self.dlratio:.3e}\n'
-                f'\nVoigt-profiles extent (extent, in HWHMs): {self.extent:.1f}\n'
-                f'Voigt-profiles cutoff extent (cutoff in cm-1): {self.cutoff:.1f}\n')
-        with np.printoptions(edgeitems=2, threshold=4):
-            text += (
-                'Voigt-profile half-sizes (size) of shape [nlor, ndop]:\n'
-                f'{self.size}\n'
-                'Voigt-profile indices (index) of shape [nlor, ndop]:\n'
-                f'{self.index}\n')
-        return text
+        """Same text as the reference's Voigt.__str__ (pyrat/voigt.py:154-194; pinned by the
+        reference's tests/test_str.py:338-366)."""
+        from .tools import Formatted_Write
+        fw = Formatted_Write(fmt={'float': '{:.3e}'.format}, edge=3)
+        fw.write('Voigt-profile information:')
+        fw.write('\nNumber of Doppler-width samples (ndop): {:d}', self.ndop)
+        fw.write('Number of Lorentz-width samples (nlor): {:d}', self.nlor)
+        fw.write('Doppler HWHM (doppler, cm-1):\n    {}', self.doppler)
+        fw.write('Lorentz HWMH (lorentz, cm-1):\n    {}', self.lorentz)
+        fw.write(f'Doppler--Lorentz ratio threshold (dlratio): {self.dlratio:.3e}')
+        fw.write(f"\nVoigt-profiles extent (extent, in HWHMs): {self.extent:.1f}")
+        fw.write(f"Voigt-profiles cutoff extent (cutoff in cm-1): {self.cutoff:.1f}")
+        fw.write('Voigt-profile half-sizes (size) of shape [nlor, ndop]:\n{}', self.size,
+                 edge=2)
+        fw.write('Voigt-profile indices (index) of shape [nlor, ndop]:\n{}', self.index,
+                 edge=2)
+        index, size = self.index[0, 0], 2 * self.size[0, 0] + 1
+        fw.write('\nVoigt profiles:\n  profile[ 0, 0]: {}', self.profile[index:index+size],
+                 fmt={'float': '{:.5e}'.format}, edge=2)
+        index = self.index[self.nlor-1, self.ndop-1]
+        size = 2 * self.size[self.nlor-1, self.ndop-1] + 1
+        fw.write('  ...\n  profile[{:2d},{:2d}]: {}', self.nlor-1, self.ndop-1,
+                 self.profile[index:index+size], fmt={'float': '{:.5e}'.format}, edge=2)
+        return fw.text

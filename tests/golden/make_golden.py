@@ -156,7 +156,8 @@ verb = 1
     ec_layer = np.copy(lbl.calc_extinction_coefficient(atm.temp, dens, layer=31))
     ec_skip = np.copy(lbl.calc_extinction_coefficient(atm.temp, dens, skip_mol=['H2O']))
     np.savez_compressed(os.path.join(HERE, "mock_forward.npz"), ec_all=ec_all,
-                        ec_layer31=ec_layer, ec_skip=ec_skip, temp=atm.temp, d=atm.d)
+                        ec_layer31=ec_layer, ec_skip=ec_skip, temp=atm.temp, d=atm.d,
+                        lbl_str=np.array(str(lbl).replace(str(lbl.tlifile), "['TLI']")))
 
     # 4. Line_Sample on the table ---------------------------------------------------------------
     ls = op.Line_Sample(ex.sampled_cs[0])

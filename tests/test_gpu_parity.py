@@ -123,6 +123,8 @@ def test_voigt_known_answer_of_reference_test_str():
     nz = want > 0
     assert np.max(np.abs(got[nz] / want[nz] - 1.0)) < TOL_VOIGT
     assert np.all(got[~nz] == 0.0)
+    # the whole known-answer string of the reference's test
+    assert str(v) == str(g["voigt_str"])
     eng.close()
 
 

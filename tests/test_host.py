@@ -295,3 +295,29 @@ def test_unit_costs_balance_table_partition():
     assert sorted(np.concatenate(parts)) == list(range(len(cost)))
     loads = np.array([cost[p].sum() for p in parts])
     assert loads.max() / loads.min() < 1.03
+
+
+def test_str_of_voigt_and_line_by_line_match_reference():
+    """`str()` of the reference-shaped objects: the Voigt text pinned by the reference's
+    tests/test_str.py:338-366 (golden string + grid from the reference run; the profile values
+    are the golden edge profiles, no GPU needed) and the Line_By_Line text for the mock TLI."""
+    from types import SimpleNamespace
+    from pyratbay_b200.spectrum import Spectrum
+    from pyratbay_b200.voigt import Voigt
+    from pyratbay_b200.line_by_line import Line_By_Line
+    g = helpers.golden("voigt_h2o_1.1-1.7um.npz")
+    spec = Spectrum(wl_low=1.1 * pc.um, wl_high=1.7 * pc.um, wnstep=1.0, wnosamp=2160)
+    atm = helpers.mock_atmosphere()
+    v = Voigt(spec, atm, np.full(4, 5), None, extent=100.0, cutoff=25.0)
+    v.size, v.index = g["size"], g["index"]
+    prof = np.zeros(int(g["profile_len"]))
+    for key, (m, n) in {"profile_first": (0, 0), "profile_last": (-1, -1)}.items():
+        prof[v.index[m, n]:v.index[m, n] + len(g[key])] = g[key]
+    v._profile = prof
+    assert str(v) == str(g["voigt_str"])
+
+    case = helpers.mock_case(with_profile=False)
+    fake = SimpleNamespace(spec=case.spec, atm=case.atm)
+    lbl = Line_By_Line(case.tlifile, case.atm.species, case.spec.wnlow, case.spec.wnhigh, fake)
+    want = str(helpers.golden("mock_forward.npz")["lbl_str"])
+    assert str(lbl).replace(str(lbl.tlifile), "['TLI']") == want
