@@ -1063,14 +1063,25 @@ static int interp_impl(int device, double *ext, const double *etable, bool on_de
         PB_CUDA(cudaStreamCreate(&st));
         own_stream = true;
     }
-    DevBuf<int> d_tlo;
-    DevBuf<double> d_wlo, d_whi, d_dens, d_tab, d_ext;
+    // Per-layer scalars in ONE stream-ordered allocation (no device-wide sync on the
+    // device-resident path): [w_lo | w_hi | density | tlo].
+    DevBuf<double> d_tab, d_ext;
     const size_t tab_n = (size_t)nspec * ntemp * nlayers * (size_t)nwave;
     const size_t ext_n = (size_t)(per_mol ? nspec : 1) * nlayers * (size_t)nwave;
-    rc = d_tlo.upload(tlo.data(), nlayers, st);
-    if (!rc) rc = d_wlo.upload(w_lo.data(), nlayers, st);
-    if (!rc) rc = d_whi.upload(w_hi.data(), nlayers, st);
-    if (!rc) rc = d_dens.upload(density, (size_t)nlayers * nspec, st);
+    const size_t ndbl = (size_t)nlayers * (2 + nspec);
+    std::vector<double> packed(ndbl + ((size_t)nlayers + 1) / 2);
+    std::copy(w_lo.begin(), w_lo.end(), packed.begin());
+    std::copy(w_hi.begin(), w_hi.end(), packed.begin() + nlayers);
+    std::copy(density, density + (size_t)nlayers * nspec, packed.begin() + 2 * (size_t)nlayers);
+    std::memcpy(packed.data() + ndbl, tlo.data(), sizeof(int) * nlayers);
+    double *d_small = nullptr;
+    {
+        cudaError_t ea = cudaMallocAsync((void **)&d_small, sizeof(double) * packed.size(), st);
+        if (ea == cudaSuccess)
+            ea = cudaMemcpyAsync(d_small, packed.data(), sizeof(double) * packed.size(),
+                                 cudaMemcpyHostToDevice, st);
+        if (ea != cudaSuccess) rc = cuda_fail(ea, "interp scalars", __FILE__, __LINE__);
+    }
     const double *tab = etable;
     double *dext = ext;
     if (!on_device) {
@@ -1080,8 +1091,10 @@ static int interp_impl(int device, double *ext, const double *etable, bool on_de
         dext = d_ext.p;
     }
     if (!rc)
-        rc = launch_interp_ec(st, dext, tab, d_tlo.p, d_wlo.p, d_whi.p, d_dens.p, nspec, ntemp,
+        rc = launch_interp_ec(st, dext, tab, (const int *)(d_small + ndbl), d_small,
+                              d_small + nlayers, d_small + 2 * (size_t)nlayers, nspec, ntemp,
                               nlayers, nwave, lay1, lay2, per_mol);
+    if (d_small) cudaFreeAsync(d_small, st);
     if (!rc && !on_device) {
         cudaError_t e2 = cudaMemcpyAsync(ext, dext, sizeof(double) * ext_n,
                                          cudaMemcpyDeviceToHost, st);
