@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdint>
 #include <vector>
 
 namespace pb200 {
@@ -414,29 +415,61 @@ counters_kernel(StaticView V, const UnitParams *__restrict__ units,
 // ---------------------------------------------------------------------------------------
 // Table interpolation in temperature.  grid = (wave chunks, layers); bit-exact with the
 // reference's operation order: ext += (tab_lo*e1 + tab_hi*e2) for each species in turn.
+template <int VEC>
 __global__ void __launch_bounds__(256)
 interp_ec_kernel(double *__restrict__ ext, const double *__restrict__ table,
                  const int *__restrict__ tlo, const double *__restrict__ w_lo,
                  const double *__restrict__ w_hi, const double *__restrict__ density,
                  int nspec, int ntemp, int nlayers, int nwave, int lay1, int per_mol) {
+    // VEC = 2: two adjacent samples per thread through 16-byte loads (nwave even, so every row
+    // of the table and of ext is 16-byte aligned); VEC = 1: generic.
     const int k = lay1 + blockIdx.y;
     const int lo = tlo[k];
     const double wl = w_lo[k], wh = w_hi[k];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwave; i += gridDim.x * blockDim.x) {
-        double acc = per_mol ? 0.0 : ext[(size_t)k * nwave + i];
+    const size_t tstride = (size_t)nlayers * nwave;  // table[j][t+1] - table[j][t]
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < nwave;
+         i += gridDim.x * blockDim.x * VEC) {
+        double acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) acc[v] = 0.0;
+        if (!per_mol) {
+            if (VEC == 2) {
+                const double2 a = *reinterpret_cast<const double2 *>(ext + (size_t)k * nwave + i);
+                acc[0] = a.x;
+                acc[VEC - 1] = a.y;
+            } else {
+                acc[0] = ext[(size_t)k * nwave + i];
+            }
+        }
         for (int j = 0; j < nspec; j++) {
             const double d = density[(size_t)k * nspec + j];
             const double e1 = dmul(wl, d), e2 = dmul(wh, d);
             const double *r = table + (((size_t)j * ntemp + lo) * nlayers + k) * (size_t)nwave + i;
-            const double v = dadd(dmul(r[0], e1), dmul(r[(size_t)nlayers * nwave], e2));
-            if (per_mol) {
-                double *dst = ext + ((size_t)j * nlayers + k) * (size_t)nwave + i;
-                *dst = dadd(*dst, v);
+            double a[VEC], b[VEC];
+            if (VEC == 2) {
+                const double2 a2 = *reinterpret_cast<const double2 *>(r);
+                const double2 b2 = *reinterpret_cast<const double2 *>(r + tstride);
+                a[0] = a2.x; a[VEC - 1] = a2.y;
+                b[0] = b2.x; b[VEC - 1] = b2.y;
             } else {
-                acc = dadd(acc, v);
+                a[0] = r[0];
+                b[0] = r[tstride];
+            }
+            double *dst = ext + ((size_t)j * nlayers + k) * (size_t)nwave + i;
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                const double val = dadd(dmul(a[v], e1), dmul(b[v], e2));
+                if (per_mol) dst[v] = dadd(dst[v], val);
+                else acc[v] = dadd(acc[v], val);
             }
         }
-        if (!per_mol) ext[(size_t)k * nwave + i] = acc;
+        if (!per_mol) {
+            if (VEC == 2)
+                *reinterpret_cast<double2 *>(ext + (size_t)k * nwave + i) =
+                    make_double2(acc[0], acc[VEC - 1]);
+            else
+                ext[(size_t)k * nwave + i] = acc[0];
+        }
     }
 }
 
@@ -516,11 +549,18 @@ int launch_interp_ec(cudaStream_t st, double *ext, const double *table, const in
                      const double *w_lo, const double *w_hi, const double *density, int nspec,
                      int ntemp, int nlayers, int nwave, int lay1, int lay2, int per_mol) {
     if (lay2 <= lay1 || nwave == 0) return 0;
-    int bx = (nwave + 255) / 256;
+    const bool vec2 = (nwave % 2 == 0) && ((uintptr_t)ext % 16 == 0) && ((uintptr_t)table % 16 == 0);
+    const int per_thread = vec2 ? 2 : 1;
+    int bx = (nwave / per_thread + 255) / 256;
     if (bx > 1024) bx = 1024;
+    if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, (unsigned)(lay2 - lay1));
-    interp_ec_kernel<<<grid, 256, 0, st>>>(ext, table, tlo, w_lo, w_hi, density, nspec, ntemp,
-                                           nlayers, nwave, lay1, per_mol);
+    if (vec2)
+        interp_ec_kernel<2><<<grid, 256, 0, st>>>(ext, table, tlo, w_lo, w_hi, density, nspec,
+                                                  ntemp, nlayers, nwave, lay1, per_mol);
+    else
+        interp_ec_kernel<1><<<grid, 256, 0, st>>>(ext, table, tlo, w_lo, w_hi, density, nspec,
+                                                  ntemp, nlayers, nwave, lay1, per_mol);
     PB_CUDA(cudaGetLastError());
     return 0;
 }

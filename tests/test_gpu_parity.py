@@ -310,8 +310,13 @@ def test_error_behaviour():
 def test_interp_ec_bit_exact_vs_oracle():
     from pyratbay_b200.engine import interp_ec, interp_ec_per_mol
     orc = helpers.oracle_module()
+    for nwave in (1000, 777):       # even: 16-byte vector path, odd: scalar path
+        _check_interp_bit_exact(interp_ec, interp_ec_per_mol, orc, nwave)
+
+
+def _check_interp_bit_exact(interp_ec, interp_ec_per_mol, orc, nwave):
     rng = np.random.default_rng(3)
-    nspec, ntemp, nlayers, nwave = 3, 7, 11, 1000
+    nspec, ntemp, nlayers = 3, 7, 11
     table = rng.uniform(1e-30, 1e-18, (nspec, ntemp, nlayers, nwave))
     tgrid = np.linspace(300.0, 3000.0, ntemp)
     temp = rng.uniform(300.0, 3000.0, nlayers)
