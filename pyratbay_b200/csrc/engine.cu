@@ -88,6 +88,43 @@ static int nearest_bisect(const double *a, double v, int lo, int hi) {
     return (std::fabs(a[hi] - v) < std::fabs(a[lo] - v)) ? hi : lo;
 }
 
+// Host replica of the device's nearest_index (common.cuh): clamp, bisection on a[mid] < v,
+// closer end with ties to the lower index.
+static int nearest_index_host(const double *a, int n, double v) {
+    if (v < a[0]) return 0;
+    if (a[n - 1] < v) return n - 1;
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        const int mid = (hi + lo) >> 1;
+        if (a[mid] < v) lo = mid; else hi = mid;
+    }
+    return (std::fabs(a[hi] - v) < std::fabs(a[lo] - v)) ? hi : lo;
+}
+
+// thr[j] = smallest double v with nearest_index(a, n, v) >= j, found by bisection on the bit
+// pattern (positive doubles order like their bits; the predicate is monotonic in v because
+// RN(a[hi]-v) and RN(v-a[lo]) are).  Empty when the grid is not strictly increasing/positive.
+static std::vector<double> nearest_thresholds(const double *a, int n) {
+    std::vector<double> thr;
+    if (n < 2 || !(a[0] > 0.0)) return thr;
+    for (int j = 1; j < n; j++)
+        if (!(a[j] > a[j - 1]) || !std::isfinite(a[j])) return thr;
+    thr.assign(n, 0.0);
+    for (int j = 1; j < n; j++) {
+        uint64_t lo, hi;  // nearest(lo) < j <= nearest(hi)
+        std::memcpy(&lo, &a[j - 1], 8);
+        std::memcpy(&hi, &a[j], 8);
+        while (hi - lo > 1) {
+            const uint64_t mid = lo + (hi - lo) / 2;
+            double v;
+            std::memcpy(&v, &mid, 8);
+            if (nearest_index_host(a, n, v) >= j) hi = mid; else lo = mid;
+        }
+        std::memcpy(&thr[j], &hi, 8);
+    }
+    return thr;
+}
+
 }  // namespace pb200
 
 using namespace pb200;
@@ -122,6 +159,9 @@ struct pb200_engine {
     DevBuf<double> d_tprofile;
     DevBuf<long long> d_tbase;
     DevBuf<int> d_trow;
+    DevBuf<ProfileSlot> d_pslot, d_tslot;
+    DevBuf<double> d_dop_thr;
+    bool has_dop_thr = false;
 
     // species
     bool has_species = false;
@@ -171,6 +211,9 @@ struct pb200_engine {
             if (c < 2.0e9) V.cut_fine = (int)c;
         }
         V.doppler = d_doppler.p;
+        V.dop_thr = has_dop_thr ? d_dop_thr.p : nullptr;
+        V.pslot = d_pslot.p;
+        V.tslot = d_tslot.p;
         V.nlor = nlor;
         V.ndop = ndop;
         V.dop_hi0 = 0;
@@ -198,6 +241,7 @@ struct pb200_engine {
         V.gbin = d_gbin.p;
         V.nbins = nbins;
         V.binw = binw;
+        V.fd_binw.set(binw);
         V.niso = niso;
         V.iso_ratio = d_iso_ratio.p;
         return V;
@@ -327,6 +371,12 @@ static int adopt_voigt_tables(pb200_engine *e, int nlor, int ndop, const double 
     if (!rc) rc = e->d_pmaxrow.upload(pmaxrow.data(), pmaxrow.size(), e->stream);
     if (!rc) rc = e->d_pindex.upload(e->pindex.data(), e->pindex.size(), e->stream);
     if (!rc) rc = e->d_doppler.upload(doppler, (size_t)ndop, e->stream);
+    std::vector<ProfileSlot> pslot(e->psize.size());
+    for (size_t i = 0; i < pslot.size(); i++) pslot[i] = ProfileSlot{e->pindex[i], e->psize[i], 0};
+    if (!rc) rc = e->d_pslot.upload(pslot.data(), pslot.size(), e->stream);
+    const std::vector<double> thr = nearest_thresholds(doppler, ndop);
+    e->has_dop_thr = !thr.empty();
+    if (!rc && e->has_dop_thr) rc = e->d_dop_thr.upload(thr.data(), thr.size(), e->stream);
     if (rc) return rc;
     PB_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
@@ -657,6 +707,9 @@ static int ensure_transposed(pb200_engine *e, int stride) {
     int rc = e->d_tprofile.alloc((size_t)total);
     if (!rc) rc = e->d_tbase.upload(tbase.data(), nslot, e->stream);
     if (!rc) rc = e->d_trow.upload(trow.data(), nslot, e->stream);
+    std::vector<ProfileSlot> tslot(nslot);
+    for (size_t at = 0; at < nslot; at++) tslot[at] = ProfileSlot{tbase[at], e->psize[at], trow[at]};
+    if (!rc) rc = e->d_tslot.upload(tslot.data(), nslot, e->stream);
     if (rc) return rc;
     rc = launch_transpose(e->stream, (int)src.size(), src.data(), dst.data(), nbin.data(),
                           rowlen.data(), total, stride, e->d_profile.p, e->d_tprofile.p);
@@ -760,6 +813,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         UnitParams &U = units[u];
         U.ofactor = ofactor;
         U.dwnstep = ownstep * ofactor;
+        U.inv_dwnstep = 1.0 / U.dwnstep;
         U.dnwn = (int)(1 + (onwn - 1) / ofactor);
         U.cut_steps = cutoff / U.dwnstep;
         U.scale = (int)std::round(wnstep / ownstep / ofactor);
@@ -891,6 +945,14 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         const char *env = std::getenv("PB200_KSPLIT");
         if (env && std::atoi(env) >= 1) ksplit = std::min(64, std::atoi(env));
     }
+    // Constant-step grids run the chunk-owned kernel (32-bit table offsets: the output-stride
+    // table plus the output grid must stay below 2^31 samples); PB200_ACC_KERNEL=owner keeps
+    // the output-owned kernel (the GPU tests compare the two).
+    int chunked = ((long long)e->d_tprofile.n + nwave < 0x7fffffffLL) ? 1 : 0;
+    {
+        const char *env = std::getenv("PB200_ACC_KERNEL");
+        if (env && std::strcmp(env, "owner") == 0) chunked = 0;
+    }
     float ms_strengths = 0.f, ms_accum = 0.f;
     // order units by strengths pass
     std::vector<int> order(n_units);
@@ -941,7 +1003,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
             if (rc) return rc;
             rc = launch_accumulate(st, V, nu, e->d_units.p + u0, e->d_iso_units.p + u0 * niso,
                                    e->d_iso_row.p, e->d_ksum.p, e->d_kmax.p, nrows, ethresh,
-                                   cutoff, cmode[u0], d_out, ksplit, e->d_partial.p);
+                                   cutoff, cmode[u0], d_out, ksplit, e->d_partial.p, chunked);
             if (rc) return rc;
             e->launches += ksplit > 1 ? 2 : 1;
             if (counters) {

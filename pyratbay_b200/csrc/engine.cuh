@@ -14,9 +14,11 @@ constexpr int kMaxIso = 256;
 struct FastDiv {
     unsigned mul = 0, shr = 0;
     int d = 1;
+    int one = 1;  // 1 when d == 1 (then mul == 0 and the quotient is n itself)
     void set(int denom) {
         d = denom;
-        if (denom <= 1) { mul = 0; shr = 0; d = 1; return; }
+        one = 0;
+        if (denom <= 1) { mul = 0; shr = 0; d = 1; one = 1; return; }
         unsigned lg = 0;
         while ((1ull << lg) < (unsigned long long)denom) lg++;  // ceil(log2(denom))
         const unsigned p = 31 + lg;
@@ -24,19 +26,29 @@ struct FastDiv {
         shr = p - 32;
     }
 #ifdef __CUDACC__
+    // All four are branch-free (the sign is folded in with masks).
     __device__ __forceinline__ int div(int n) const {  // 0 <= n < 2^31
-        return d == 1 ? n : (int)(__umulhi((unsigned)n, mul) >> shr);
+        return (int)(__umulhi((unsigned)n, mul) >> shr) + n * one;
     }
     __device__ __forceinline__ int div_trunc(int n) const {  // C semantics, any sign
-        return n >= 0 ? div(n) : -div(-n);
+        const int s = n >> 31;
+        return (div((n ^ s) - s) ^ s) - s;
     }
     __device__ __forceinline__ int div_ceil(int n) const {  // n >= 0
         return div(n + d - 1);
     }
     __device__ __forceinline__ int div_floor(int n) const {  // any sign
-        return n >= 0 ? div(n) : -div(-n + d - 1);
+        const int s = n >> 31;
+        return (div(((n ^ s) - s) + (s & (d - 1))) ^ s) - s;
     }
 #endif
+};
+
+// Per-profile descriptor read with one 16-byte load.
+struct __align__(16) ProfileSlot {
+    long long base;  // start of the profile (reference layout) or of its transposed block
+    int half;        // half size (aliases resolved)
+    int rowlen;      // transposed block: row length Q; reference layout: unused
 };
 
 // Device view of everything that does not depend on (T,p).  Passed to kernels by value.
@@ -53,6 +65,10 @@ struct StaticView {
     const int *pmaxrow;        // [nlor*ndop] running maximum of psize along the Doppler axis
     int cut_fine;              // cutoff in fine samples (+1), INT_MAX when there is no cutoff
     const double *doppler;     // [ndop]
+    // dop_thr[j] = smallest double v whose nearest Doppler sample is >= j (thr[0] = 0): the
+    // nearest index is a step function of v, so the O(log n) search becomes one or two
+    // comparisons.  NULL when the grid is not strictly increasing (generic search then).
+    const double *dop_thr;
     int nlor, ndop;
     int dop_hi0;               // high word of doppler[0]            (nearest_index_log)
     float dop_inv_step;        // (ndop-1)/log2(doppler[-1]/doppler[0])/2^20
@@ -62,6 +78,8 @@ struct StaticView {
     const double *tprofile;
     const long long *tbase;    // [nlor*ndop] start of the profile's transposed block
     const int *trow;           // [nlor*ndop] row length Q = ceil((2*size+1)/tstride)
+    const ProfileSlot *pslot;  // [nlor*ndop] {pindex, half, -} : one 16-byte load per group
+    const ProfileSlot *tslot;  // [nlor*ndop] {tbase, half, trow}
     int tstride;               // fine samples per output sample (0: no transposed copy)
     FastDiv fd_tstride;
     // co-add groups (sorted by isotope, then wavenumber)
@@ -74,6 +92,7 @@ struct StaticView {
     // per-isotope coarse index: gbin[iso*(nbins+1)+b] = first group with iown >= b*binw
     const int *gbin;
     int nbins, binw;
+    FastDiv fd_binw;
     int niso;
     const double *iso_ratio;  // [niso]
 };
@@ -81,6 +100,7 @@ struct StaticView {
 // Per-(T,p) unit quantities computed on the host exactly as _extcoeff.c:138-200 does.
 struct UnitParams {
     double dwnstep;    // ownstep*ofactor                 (:194)
+    double inv_dwnstep;  // RN(1/dwnstep): (w-own0)/dwnstep is formed from it exactly (quotient_rn)
     double cut_steps;  // cutoff/dwnstep                  (:295,297)
     int tpass;         // strengths pass (distinct T, Z) within the current chunk
     int ofactor;       // dynamic oversampling divisor    (:193)

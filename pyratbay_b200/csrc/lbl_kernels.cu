@@ -35,20 +35,35 @@ struct Prep {
     int lo, hi;      // coordinate range [lo, hi): dynamic index j, or output index m (kTransposed)
 };
 
+// Nearest Doppler sample of width v.  `s_dop` is the shared-memory copy of the threshold
+// table (V.dop_thr) when the grid has one, of the grid itself otherwise.
+__device__ __forceinline__ int doppler_index(const StaticView &V, const double *s_dop, double v) {
+    return V.dop_thr ? nearest_index_thr(s_dop, V.ndop, v, V.dop_hi0, V.dop_inv_step)
+                     : nearest_index_log(s_dop, V.ndop, v, V.dop_hi0, V.dop_inv_step);
+}
+
+__device__ __forceinline__ ProfileSlot load_slot(const ProfileSlot *p) {
+    const int4 raw = __ldg(reinterpret_cast<const int4 *>(p));
+    ProfileSlot s;
+    s.base = (long long)(((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x);
+    s.half = raw.z;
+    s.rowlen = raw.w;
+    return s;
+}
+
 // The per-group part of _extcoeff.c:264-299, identical integer/floating-point decisions.
 template <int MODE>
 __device__ __forceinline__ bool prepare_group(const StaticView &V, const UnitParams &U,
-                                              const IsoUnit &I, const double *s_doppler,
+                                              const IsoUnit &I, const double *s_dop,
                                               double kthr, double cutoff, double w, int iown,
                                               double k, Prep *out) {
     if (k < kthr) return false;  // :265 skip weak lines
     k = dmul(k, I.dens);         // :271-272 (dens == 1 when add == 0)
-    const int idwn = (int)ddiv(dsub(w, V.own0), U.dwnstep);                 // :275
-    const int idop = (V.ndop >= 2)                                          // :278
-        ? nearest_index_log(s_doppler, V.ndop, dmul(I.adop, w), V.dop_hi0, V.dop_inv_step)
-        : 0;
+    const int idwn = (int)quotient_rn(dsub(w, V.own0), U.dwnstep, U.inv_dwnstep);  // :275
+    const int idop = (V.ndop >= 2) ? doppler_index(V, s_dop, dmul(I.adop, w)) : 0;  // :278
     const int at = I.ilor * V.ndop + idop;
-    const int half = V.psize[at];
+    const ProfileSlot ps = load_slot((MODE == kTransposed ? V.tslot : V.pslot) + at);
+    const int half = ps.half;
     const int sub = iown - idwn * U.ofactor;                                // :281
     int jlo = idwn - U.fd_ofactor.div_trunc(half - sub);                    // :286
     int jhi = idwn + U.fd_ofactor.div_trunc(half + sub);                    // :287
@@ -70,11 +85,11 @@ __device__ __forceinline__ bool prepare_group(const StaticView &V, const UnitPar
         const int d = half - iown;
         const int q0 = V.fd_tstride.div_floor(d);
         const int r = d - q0 * V.tstride;
-        out->base = V.tbase[at] + (long long)r * V.trow[at] + q0;
+        out->base = ps.base + (long long)r * ps.rowlen + q0;
         out->lo = mlo;
         out->hi = mhi;
     } else {
-        out->base = V.pindex[at] + (long long)half - (long long)iown;       // :283,303
+        out->base = ps.base + (long long)half - (long long)iown;            // :283,303
         out->lo = jlo;
         out->hi = jhi;
     }
@@ -153,6 +168,10 @@ strengths_kernel(StaticView V, const double *__restrict__ tp_temp,
 #ifndef PB200_UNROLL
 #define PB200_UNROLL 8
 #endif
+#ifndef PB200_PACKED
+#define PB200_PACKED 1   // 16-byte packed staging for constant-step grids (needs tlen < 2^32)
+#endif
+constexpr unsigned kPackBias = 64;
 #ifdef PB200_MINBLOCKS
 #define PB200_ACC_BOUNDS __launch_bounds__(256, PB200_MINBLOCKS)
 #else
@@ -175,7 +194,8 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
     __shared__ double2 s_kp[8][32];
     __shared__ int2 s_r[8][32];
 
-    for (int i = threadIdx.x; i < V.ndop; i += blockDim.x) s_doppler[i] = V.doppler[i];
+    for (int i = threadIdx.x; i < V.ndop; i += blockDim.x)
+        s_doppler[i] = V.dop_thr ? V.dop_thr[i] : V.doppler[i];
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -211,6 +231,12 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
     xmax = __reduce_max_sync(0xffffffffu, xmax);
     // byte offset of this lane's sample(s) from a staged group's base address
     const long long off0 = (long long)mult * x0 * 8, off1 = (long long)mult * x1 * 8;
+#if PB200_PACKED
+    // packed staging (kTransposed): lane l of an active warp owns output xmin + l
+    const unsigned lanebit = (MODE == kTransposed && x0 >= 0) ? (1u << (x0 - xmin)) : 0u;
+    const double *__restrict__ lane_ptr =
+        V.tprofile + (x0 >= 0 ? x0 - xmin : 0) - (long long)kPackBias;
+#endif
 
     double acc0 = 0.0, acc1 = 0.0;
     if (xmax >= xmin) {
@@ -225,8 +251,7 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
             int reach = I.reach;
             if (V.ndop >= 2) {
                 const double wn_hi = dadd(V.own0, dmul((double)min(fhi, V.onwn - 1), V.ownstep));
-                const int nhi = min(V.ndop - 1, 1 + nearest_index_log(
-                    s_doppler, V.ndop, dmul(I.adop, wn_hi), V.dop_hi0, V.dop_inv_step));
+                const int nhi = min(V.ndop - 1, 1 + doppler_index(V, s_doppler, dmul(I.adop, wn_hi)));
                 reach = min(reach, min(V.pmaxrow[I.ilor * V.ndop + nhi], V.cut_fine) +
                                        2 * U.ofactor + 2);
             }
@@ -236,8 +261,8 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
             if (flo < 0) flo = 0;
             if (fhi > V.onwn - 1) fhi = V.onwn - 1;
             const int *gb = V.gbin + (size_t)iso * (V.nbins + 1);
-            const int glo = gb[(int)(flo / V.binw)];
-            const int ghi = gb[(int)(fhi / V.binw) + 1];
+            const int glo = gb[V.fd_binw.div((int)flo)];
+            const int ghi = gb[V.fd_binw.div((int)fhi) + 1];
             const double kthr =
                 dmul(ethresh, __longlong_as_double((long long)kmax[(size_t)U.tpass * nrows + row]));
             // inputs of the first chunk; each later chunk's are requested one chunk ahead so
@@ -266,11 +291,35 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
                                         &p);
                 // clip to the coordinates this warp owns so that empty slots cost nothing more
                 const int lo = max(p.lo, xmin), hi = min(p.hi, xmax + 1);
+                const int n = min(32, ghi - c);
+#if PB200_PACKED
+                if (MODE == kTransposed) {
+                    // Packed staging (constant-step grids: the warp's outputs are consecutive,
+                    // lane l owns output xmin+l): one 16-byte word per group
+                    //   {k, table offset of the sample of output xmin (+bias), lane mask}
+                    // read with a single broadcast LDS.128; a lane tests its mask bit.
+                    unsigned mask = 0u;
+                    if (hi > lo) mask = (0xffffffffu >> (32 - (hi - lo))) << (lo - xmin);
+                    const unsigned off = (unsigned)(p.base + xmin + (long long)kPackBias);
+                    s_kp[warp][lane] = make_double2(
+                        p.k, __longlong_as_double((long long)(((unsigned long long)mask << 32) | off)));
+                    __syncwarp();
+PB200_PRAGMA_UNROLL
+                    for (int t = 0; t < n; t++) {
+                        const double2 sl = s_kp[warp][t];
+                        const unsigned long long bits =
+                            (unsigned long long)__double_as_longlong(sl.y);
+                        if ((unsigned)(bits >> 32) & lanebit)
+                            acc0 = fma(sl.x, __ldg(lane_ptr + (unsigned)bits), acc0);
+                    }
+                    __syncwarp();
+                    continue;
+                }
+#endif
                 s_kp[warp][lane] = make_double2(
                     p.k, __longlong_as_double((long long)(table + p.base)));
                 s_r[warp][lane] = make_int2(lo, hi > lo ? hi - lo : 0);
                 __syncwarp();
-                const int n = min(32, ghi - c);
 PB200_PRAGMA_UNROLL
                 for (int t = 0; t < n; t++) {
                     const int2 r = s_r[warp][t];
@@ -301,6 +350,262 @@ PB200_PRAGMA_UNROLL
         } else {
             dst[m] = acc0;  // 0 beyond mcount
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel 3b: chunk-owned accumulation for constant-step grids (the output-stride table).
+//
+// The output-owned kernel above spends most of its slots on lanes that lie outside a
+// group's footprint: a warp that owns 32 fixed outputs visits every chunk of 32 groups whose
+// footprint [a, a+F) overlaps them, i.e. (32+F)/32 warp visits per chunk for F useful lanes.
+// Consecutive groups (sorted by wavenumber) have almost the same footprint, so here a warp
+// owns a CHUNK of 32 groups instead and places its lanes on the chunk's own footprint
+// [lo_min, hi_max): ceil(F/32) passes per chunk, every pass with (nearly) all lanes inside.
+// Chunks whose footprint is <= 16 (<= 8) outputs wide run two (four) groups per instruction
+// on half (quarter) warps.  A pass accumulates its 32 slots in a register and adds the sum
+// once to the warp's PRIVATE copy of the CTA's 256-output tile in shared memory; the eight
+// copies are summed in a fixed order at the end (no atomics, deterministic).
+// The chunk list of a tile (all isotopes) is split evenly over the 8*ksplit warps working
+// on the tile, so the work of a CTA is balanced whatever the line density.
+// Staged slot (16 bytes, one broadcast LDS.128): {k, table offset of the sample of output
+// lo_min (int32), lane mask of the current pass}.  Needs tlen + nwave < 2^31.
+#ifndef PB200_CHUNK_UNROLL
+#define PB200_CHUNK_UNROLL 16
+#endif
+#ifndef PB200_CHUNK_MINBLOCKS
+#define PB200_CHUNK_MINBLOCKS 4
+#endif
+#define PB200_CHUNK_BOUNDS __launch_bounds__(256, PB200_CHUNK_MINBLOCKS)
+
+// One empty asm that "modifies" all N values: everything that produces them (the gathers) is
+// scheduled before it, everything that consumes them after it.
+template <int N>
+__device__ __forceinline__ void issue_fence(double (&v)[N]) {
+    static_assert(N == 2 || N == 4 || N == 8 || N == 16, "unsupported unroll");
+    if constexpr (N == 2) {
+        asm volatile("" : "+d"(v[0]), "+d"(v[1]));
+    } else if constexpr (N == 4) {
+        asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]));
+    } else if constexpr (N == 8) {
+        asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]),
+                          "+d"(v[5]), "+d"(v[6]), "+d"(v[7]));
+    } else {
+        asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]),
+                          "+d"(v[5]), "+d"(v[6]), "+d"(v[7]), "+d"(v[8]), "+d"(v[9]),
+                          "+d"(v[10]), "+d"(v[11]), "+d"(v[12]), "+d"(v[13]), "+d"(v[14]),
+                          "+d"(v[15]));
+    }
+}
+
+// Run the staged slots of one pass: W lanes per slot, 32/W slots per instruction.
+template <int W>
+__device__ __forceinline__ double run_slots(const double2 *__restrict__ slots, int nslots,
+                                            const double *lane_ptr, int lane) {
+    constexpr int R = 32 / W;                      // slots per instruction
+    constexpr int U = PB200_CHUNK_UNROLL < 32 / R ? PB200_CHUNK_UNROLL : 32 / R;
+    unsigned bit = 1u << (lane & (W - 1));
+    asm volatile("" : "+r"(bit));  // keep the mask test one LOP3 (not shift + and + compare)
+    const double2 *__restrict__ mine = slots + (R > 1 ? lane / W : 0);
+    // keep the lane's table pointer in a register pair: one IMAD.WIDE per slot address
+    asm volatile("" : "+l"(lane_ptr));
+    // slots beyond nslots carry an empty mask, so the trip count is rounded up to the unroll
+    const int niter = (((nslots + R - 1) / R) + U - 1) / U * U;
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int i = 0; i < niter; i += U) {
+        // phase 1: issue all U gathers (lanes outside a slot's mask keep a zero sample)...
+        double kk[U], vv[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const double2 s = mine[(i + j) * R];
+            kk[j] = s.x;
+            vv[j] = 0.0;
+            if ((unsigned)__double2hiint(s.y) & bit) vv[j] = __ldg(lane_ptr + __double2loint(s.y));
+        }
+        // ...before the first sample is consumed (U loads in flight per warp; without this
+        // fence ptxas interleaves each FMA right behind its load)
+        issue_fence(vv);
+        // phase 2
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            if (j & 1) acc1 = fma(kk[j], vv[j], acc1);
+            else acc0 = fma(kk[j], vv[j], acc0);
+        }
+    }
+    double acc = acc0 + acc1;
+    if (W <= 16) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    if (W <= 8) acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+    return acc;
+}
+
+// Candidate groups of isotope `iso` for the outputs [xmin, xmax] of one unit (same window as
+// the output-owned kernel: coarse index, tightened with the running profile maximum).
+__device__ __forceinline__ bool candidate_range(const StaticView &V, const UnitParams &U,
+                                                const IsoUnit &I, const double *s_doppler,
+                                                int iso, int xmin, int xmax, int *glo, int *ghi) {
+    long long fhi = (long long)xmax * V.tstride + I.reach;
+    int reach = I.reach;
+    if (V.ndop >= 2) {
+        const double wn_hi = dadd(V.own0, dmul((double)min(fhi, V.onwn - 1), V.ownstep));
+        const int nhi = min(V.ndop - 1, 1 + doppler_index(V, s_doppler, dmul(I.adop, wn_hi)));
+        reach = min(reach, min(V.pmaxrow[I.ilor * V.ndop + nhi], V.cut_fine) + 2 * U.ofactor + 2);
+    }
+    long long flo = (long long)xmin * V.tstride - reach;
+    fhi = (long long)xmax * V.tstride + reach;
+    if (fhi < 0 || flo > V.onwn - 1) return false;
+    if (flo < 0) flo = 0;
+    if (fhi > V.onwn - 1) fhi = V.onwn - 1;
+    const int *gb = V.gbin + (size_t)iso * (V.nbins + 1);
+    *glo = gb[V.fd_binw.div((int)flo)];
+    *ghi = gb[V.fd_binw.div((int)fhi) + 1];
+    return *ghi > *glo;
+}
+
+__global__ void PB200_CHUNK_BOUNDS
+accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
+                         const IsoUnit *__restrict__ iso_units, const int *__restrict__ iso_row,
+                         const double *__restrict__ ksum,
+                         const unsigned long long *__restrict__ kmax, int nrows, double ethresh,
+                         double cutoff, double *__restrict__ out, int ksplit,
+                         double *__restrict__ partial) {
+    extern __shared__ double s_doppler[];           // [ndop]
+    __shared__ double s_acc[8][kTileOutputs];       // per-warp private copy of the tile
+    __shared__ double2 s_slot[8][32];
+    __shared__ int2 s_range[kMaxIso];               // candidate groups [glo, ghi) per isotope
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < V.ndop; i += blockDim.x)
+        s_doppler[i] = V.dop_thr ? V.dop_thr[i] : V.doppler[i];
+#pragma unroll
+    for (int i = 0; i < kTileOutputs / 32; i++) s_acc[warp][i * 32 + lane] = 0.0;
+    __syncthreads();
+
+    const UnitParams U = units[blockIdx.y];
+    const int row = blockIdx.z;
+    const int tile = blockIdx.x / ksplit, split = blockIdx.x - tile * ksplit;
+    const int m0 = tile * kTileOutputs;
+    const int tile_hi = min(m0 + kTileOutputs, min(V.nwave, U.mcount));  // exclusive
+    const double *__restrict__ ks = ksum + (size_t)U.tpass * V.ngroups;
+    double *acc_tile = s_acc[warp];
+    double2 *slots = s_slot[warp];
+
+    // candidate range of every isotope, one thread per isotope (niso <= kMaxIso == blockDim)
+    if (threadIdx.x < V.niso) {
+        const int iso = threadIdx.x;
+        int glo = 0, ghi = 0;
+        if (tile_hi > m0 && iso_row[iso] == row &&
+            !candidate_range(V, U, iso_units[(size_t)blockIdx.y * V.niso + iso], s_doppler, iso,
+                             m0, tile_hi - 1, &glo, &ghi))
+            glo = ghi = 0;
+        s_range[iso] = make_int2(glo, ghi);
+    }
+    __syncthreads();
+
+    if (tile_hi > m0) {
+        // this warp's share [cb, ce) of the tile's chunk list (all isotopes, concatenated)
+        long long total = 0;
+        for (int iso = 0; iso < V.niso; iso++) {
+            const int2 r = s_range[iso];
+            total += (r.y - r.x + 31) >> 5;
+        }
+        const int nworkers = 8 * ksplit, wid = split * 8 + warp;
+        const long long cb = total * wid / nworkers, ce = total * (wid + 1) / nworkers;
+        const double kmax_row =
+            __longlong_as_double((long long)kmax[(size_t)U.tpass * nrows + row]);
+        const double kthr = dmul(ethresh, kmax_row);
+        const unsigned lt = (1u << lane) - 1u;
+
+        long long cpos = 0;
+        for (int iso = 0; iso < V.niso && cpos < ce; iso++) {
+            const int glo = s_range[iso].x, ghi = s_range[iso].y;
+            const long long nchunk = (ghi - glo + 31) >> 5;
+            const long long c0 = max(cb, cpos) - cpos, c1 = min(ce, cpos + nchunk) - cpos;
+            cpos += nchunk;
+            if (c1 <= c0) continue;
+            const IsoUnit I = iso_units[(size_t)blockIdx.y * V.niso + iso];
+            const int gbeg = glo + 32 * (int)c0, gend = min(ghi, glo + 32 * (int)c1);
+
+            // inputs of the first chunk; each later chunk's are requested one chunk ahead
+            double nx_w = 0.0, nx_k = 0.0;
+            int nx_iown = 0;
+            if (gbeg + lane < gend) {
+                nx_w = V.g_wn[gbeg + lane];
+                nx_iown = V.g_iown[gbeg + lane];
+                nx_k = ks[gbeg + lane];
+            }
+            for (int c = gbeg; c < gend; c += 32) {
+                const int g = c + lane;
+                const double cur_w = nx_w, cur_k = nx_k;
+                const int cur_iown = nx_iown;
+                if (g + 32 < gend) {
+                    nx_w = V.g_wn[g + 32];
+                    nx_iown = V.g_iown[g + 32];
+                    nx_k = ks[g + 32];
+                }
+                Prep p;
+                p.k = 0.0; p.base = 0; p.lo = 0; p.hi = 0;
+                bool valid = false;
+                if (g < gend)
+                    valid = prepare_group<kTransposed>(V, U, I, s_doppler, kthr, cutoff, cur_w,
+                                                       cur_iown, cur_k, &p);
+                const int lo = max(p.lo, m0), hi = min(p.hi, tile_hi);
+                valid = valid && hi > lo;
+                const unsigned vb = __ballot_sync(0xffffffffu, valid);
+                if (vb == 0u) continue;
+                const int nval = __popc(vb);
+                const int lo_min = __reduce_min_sync(0xffffffffu, valid ? lo : INT_MAX);
+                const int hi_max = __reduce_max_sync(0xffffffffu, valid ? hi : INT_MIN);
+                const int span = hi_max - lo_min;
+                // survivors are compacted to the front; the rest fill the tail with empty masks
+                const int pos = valid ? __popc(vb & lt) : nval + __popc(~vb & lt);
+                const int a0 = valid ? lo - lo_min : 0, b0 = valid ? hi - lo_min : 0;
+                const int off = valid ? (int)(p.base + lo_min) : 0;
+                unsigned mask = 0u;
+                {
+                    const int b = min(b0, 32);
+                    if (b > a0) mask = (0xffffffffu >> (32 - (b - a0))) << a0;
+                }
+                slots[pos] = make_double2(valid ? p.k : 0.0,
+                                          __hiloint2double((int)mask, off));
+                __syncwarp();
+                if (span <= 8) {
+                    const double acc = run_slots<8>(slots, nval, V.tprofile + (lane & 7), lane);
+                    if (lane < 8 && lo_min + lane < hi_max) acc_tile[lo_min + lane - m0] += acc;
+                } else if (span <= 16) {
+                    const double acc = run_slots<16>(slots, nval, V.tprofile + (lane & 15), lane);
+                    if (lane < 16 && lo_min + lane < hi_max) acc_tile[lo_min + lane - m0] += acc;
+                } else {
+                    for (int x0 = 0; x0 < span; x0 += 32) {
+                        if (x0 > 0) {
+                            // restage the masks of this pass (k and the offset stay)
+                            const int a = max(a0, x0) - x0, b = min(b0, x0 + 32) - x0;
+                            mask = 0u;
+                            if (b > a) mask = (0xffffffffu >> (32 - (b - a))) << a;
+                            __syncwarp();
+                            reinterpret_cast<int *>(&slots[pos])[3] = (int)mask;
+                            __syncwarp();
+                            if (!__any_sync(0xffffffffu, mask != 0u)) continue;
+                        }
+                        const double acc =
+                            run_slots<32>(slots, nval, V.tprofile + x0 + lane, lane);
+                        const int x = lo_min + x0 + lane;
+                        if (x < hi_max) acc_tile[x - m0] += acc;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    const int m = m0 + threadIdx.x;
+    if (m < V.nwave) {
+        double sum = s_acc[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < 8; w++) sum += s_acc[w][threadIdx.x];
+        double *dst = ksplit > 1
+            ? partial + (((size_t)blockIdx.y * nrows + row) * ksplit + split) * (size_t)V.nwave
+            : out + ((size_t)U.out_index * nrows + row) * (size_t)V.nwave;
+        dst[m] = sum;  // 0 beyond mcount
     }
 }
 
@@ -353,7 +658,8 @@ counters_kernel(StaticView V, const UnitParams *__restrict__ units,
                 int nrows, double ethresh, double cutoff, int linterp,
                 unsigned long long *__restrict__ counters /* [units,4] */) {
     extern __shared__ double s_doppler[];
-    for (int i = threadIdx.x; i < V.ndop; i += blockDim.x) s_doppler[i] = V.doppler[i];
+    for (int i = threadIdx.x; i < V.ndop; i += blockDim.x)
+        s_doppler[i] = V.dop_thr ? V.dop_thr[i] : V.doppler[i];
     __syncthreads();
     const UnitParams U = units[blockIdx.y];
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -489,13 +795,16 @@ int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
                       const UnitParams *units, const IsoUnit *iso_units, const int *iso_row,
                       const double *ksum, const unsigned long long *kmax, int nrows,
                       double ethresh, double cutoff, int mode, double *out, int ksplit,
-                      double *partial) {
+                      double *partial, int chunked) {
     if (nunits == 0 || V.nwave == 0) return 0;
     if (ksplit < 1 || !partial) ksplit = 1;
     const int ntiles = (V.nwave + kTileOutputs - 1) / kTileOutputs;
     dim3 grid((unsigned)(ntiles * ksplit), (unsigned)nunits, (unsigned)nrows);
     const size_t smem = sizeof(double) * V.ndop;
-    if (mode == kLinterp)
+    if (mode == kTransposed && chunked)
+        accumulate_chunks_kernel<<<grid, 256, smem, st>>>(
+            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
+    else if (mode == kLinterp)
         accumulate_kernel<kLinterp><<<grid, 256, smem, st>>>(
             V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
     else if (mode == kTransposed)

@@ -178,15 +178,19 @@ def test_forward_model_matches_reference():
     dict(resolution=8000.0),                           # constant-R (2-point interpolation)
     dict(nlines=200000, wnosamp=120),                  # dense: heavy co-adding
     dict(wnstep=0.25, wnosamp=360, wnlow=9000.0, wnhigh=9060.0),
+    dict(nlines=300, wnlow=9000.0, wnhigh=9600.0),     # sparse: chunks span many outputs
 ])
-@pytest.mark.parametrize("acc_mode", ["auto", "strided"])
+@pytest.mark.parametrize("acc_mode", ["auto", "owner", "strided"])
 def test_extinction_matches_oracle_synthetic(kwargs, acc_mode, monkeypatch):
-    # "auto": coalesced gather from the output-stride Voigt table where the grid allows it;
-    # "strided": the generic gather from the reference-layout table (csrc/lbl_kernels.cu).
+    # "auto": chunk-owned kernel gathering from the output-stride Voigt table where the grid
+    # allows it; "owner": the output-owned kernel on the same table; "strided": the generic
+    # gather from the reference-layout table (csrc/lbl_kernels.cu).
+    if acc_mode != "auto" and kwargs.get("resolution"):
+        pytest.skip("constant-R grids have a single accumulate mode")
     if acc_mode == "strided":
-        if kwargs.get("resolution"):
-            pytest.skip("constant-R grids have a single accumulate mode")
         monkeypatch.setenv("PB200_ACC_MODE", "strided")
+    if acc_mode == "owner":
+        monkeypatch.setenv("PB200_ACC_KERNEL", "owner")
     case = helpers.synthetic_case(**kwargs)
     eng = _engine_for(case, profile="host")
     atm = case.atm
