@@ -704,7 +704,10 @@ static int ensure_transposed(pb200_engine *e, int stride) {
         }
     }
     e->tstride = 0;
-    int rc = e->d_tprofile.alloc((size_t)total);
+    // 256 zero samples of padding: the slot-major accumulate path reads (and multiplies by 0)
+    // up to 8*32 samples from the table start for the empty tail slots of a chunk.
+    int rc = e->d_tprofile.alloc((size_t)total + 256);
+    if (!rc) PB_CUDA(cudaMemsetAsync(e->d_tprofile.p + total, 0, 256 * sizeof(double), e->stream));
     if (!rc) rc = e->d_tbase.upload(tbase.data(), nslot, e->stream);
     if (!rc) rc = e->d_trow.upload(trow.data(), nslot, e->stream);
     std::vector<ProfileSlot> tslot(nslot);

@@ -382,15 +382,29 @@ PB200_PRAGMA_UNROLL
 // scheduled before it, everything that consumes them after it.
 template <int N>
 __device__ __forceinline__ void issue_fence(double (&v)[N]) {
-    static_assert(N == 2 || N == 4 || N == 8 || N == 16, "unsupported unroll");
+    static_assert(N % 2 == 0 && N <= 16, "unsupported unroll");
     if constexpr (N == 2) {
         asm volatile("" : "+d"(v[0]), "+d"(v[1]));
     } else if constexpr (N == 4) {
         asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]));
+    } else if constexpr (N == 6) {
+        asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]), "+d"(v[5]));
     } else if constexpr (N == 8) {
         asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]),
                           "+d"(v[5]), "+d"(v[6]), "+d"(v[7]));
+    } else if constexpr (N == 10) {
+        asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]),
+                          "+d"(v[5]), "+d"(v[6]), "+d"(v[7]), "+d"(v[8]), "+d"(v[9]));
+    } else if constexpr (N == 12) {
+        asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]),
+                          "+d"(v[5]), "+d"(v[6]), "+d"(v[7]), "+d"(v[8]), "+d"(v[9]),
+                          "+d"(v[10]), "+d"(v[11]));
+    } else if constexpr (N == 14) {
+        asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]),
+                          "+d"(v[5]), "+d"(v[6]), "+d"(v[7]), "+d"(v[8]), "+d"(v[9]),
+                          "+d"(v[10]), "+d"(v[11]), "+d"(v[12]), "+d"(v[13]));
     } else {
+        static_assert(N == 16 || N <= 14, "unsupported unroll");
         asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]),
                           "+d"(v[5]), "+d"(v[6]), "+d"(v[7]), "+d"(v[8]), "+d"(v[9]),
                           "+d"(v[10]), "+d"(v[11]), "+d"(v[12]), "+d"(v[13]), "+d"(v[14]),
@@ -436,6 +450,68 @@ __device__ __forceinline__ double run_slots(const double2 *__restrict__ slots, i
     if (W <= 16) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
     if (W <= 8) acc += __shfl_xor_sync(0xffffffffu, acc, 8);
     return acc;
+}
+
+// Slot-major form for chunks that need P passes of 32 outputs (lane l owns outputs
+// lo_min + 32p + l, p < P, in registers): ONE broadcast per slot serves all its passes, the
+// P gathers of a slot share one address (immediate offsets 256p bytes) and only the first and
+// the last pass are predicated -- every staged group starts inside pass 0 and ends inside
+// pass P-1 (checked by the caller), so the passes in between are covered by all of them.
+// Staged word 3 = a | bL << 8: first lane of pass 0, one-past-last lane of pass P-1.
+// The shared-memory/L1 data pipe is what bounds this kernel (2 cycles per broadcast, 2 per
+// 256-byte gather): P passes cost 2 + 2P instead of 4P cycles.
+template <int P>
+__device__ __forceinline__ void run_multi(const double2 *__restrict__ slots, int nslots,
+                                          const double *lane_ptr, int lane, double (&acc)[P]) {
+    constexpr int U = P == 1 ? PB200_CHUNK_UNROLL : (P == 2 ? 8 : (P <= 4 ? 4 : 2));
+    asm volatile("" : "+l"(lane_ptr));
+    const int niter = (nslots + U - 1) / U * U;  // tail slots: k = 0, offset 0 (valid address)
+#pragma unroll
+    for (int q = 0; q < P; q++) acc[q] = 0.0;
+    double odd = 0.0;  // second chain for P == 1
+    for (int i = 0; i < niter; i += U) {
+        double kk[U], vv[U * P];
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const double2 s = slots[i + j];
+            kk[j] = s.x;
+            const double *src = lane_ptr + __double2loint(s.y);
+            const int w = __double2hiint(s.y);
+            const int a = w & 0xff, bl = w >> 8;
+#pragma unroll
+            for (int q = 0; q < P; q++) {
+                bool on = true;
+                if (q == 0) on = lane >= a;
+                if (q == P - 1) on = on && lane < bl;
+                if (q == 0 || q == P - 1) {
+                    vv[j * P + q] = 0.0;
+                    if (on) vv[j * P + q] = __ldg(src + 32 * q);
+                } else {
+                    vv[j * P + q] = __ldg(src + 32 * q);
+                }
+            }
+        }
+        issue_fence(vv);
+#pragma unroll
+        for (int j = 0; j < U; j++)
+#pragma unroll
+            for (int q = 0; q < P; q++) {
+                if (P == 1 && (j & 1)) odd = fma(kk[j], vv[j * P + q], odd);
+                else acc[q] = fma(kk[j], vv[j * P + q], acc[q]);
+            }
+    }
+    if (P == 1) acc[0] += odd;
+}
+
+template <int P>
+__device__ __forceinline__ void run_multi_store(const double2 *slots, int nslots,
+                                                const double *lane_ptr, int lane,
+                                                double *acc_rel, int span) {
+    double acc[P];
+    run_multi<P>(slots, nslots, lane_ptr, lane, acc);
+#pragma unroll
+    for (int q = 0; q < P; q++)
+        if (32 * q + lane < span) acc_rel[32 * q + lane] += acc[q];
 }
 
 // Candidate groups of isotope `iso` for the outputs [xmin, xmax] of one unit (same window as
@@ -560,36 +636,60 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                 const int pos = valid ? __popc(vb & lt) : nval + __popc(~vb & lt);
                 const int a0 = valid ? lo - lo_min : 0, b0 = valid ? hi - lo_min : 0;
                 const int off = valid ? (int)(p.base + lo_min) : 0;
-                unsigned mask = 0u;
-                {
-                    const int b = min(b0, 32);
-                    if (b > a0) mask = (0xffffffffu >> (32 - (b - a0))) << a0;
-                }
-                slots[pos] = make_double2(valid ? p.k : 0.0,
-                                          __hiloint2double((int)mask, off));
-                __syncwarp();
-                if (span <= 8) {
-                    const double acc = run_slots<8>(slots, nval, V.tprofile + (lane & 7), lane);
-                    if (lane < 8 && lo_min + lane < hi_max) acc_tile[lo_min + lane - m0] += acc;
-                } else if (span <= 16) {
-                    const double acc = run_slots<16>(slots, nval, V.tprofile + (lane & 15), lane);
-                    if (lane < 16 && lo_min + lane < hi_max) acc_tile[lo_min + lane - m0] += acc;
+                const double kval = valid ? p.k : 0.0;
+                double *acc_rel = acc_tile + (lo_min - m0);
+                const int npass = (span + 31) >> 5;
+                // slot-major form: every group starts in pass 0 and ends in the last pass
+                const int bl = b0 - 32 * (npass - 1);
+                const bool multi = span > 16 && npass <= 8 &&
+                                   __all_sync(0xffffffffu, !valid || (a0 < 32 && bl >= 1));
+                if (multi) {
+                    slots[pos] = make_double2(
+                        kval, __hiloint2double(valid ? (a0 | (bl << 8)) : 32, off));
+                    __syncwarp();
+                    const double *lp = V.tprofile + lane;
+                    switch (npass) {
+                    case 1: run_multi_store<1>(slots, nval, lp, lane, acc_rel, span); break;
+                    case 2: run_multi_store<2>(slots, nval, lp, lane, acc_rel, span); break;
+                    case 3: run_multi_store<3>(slots, nval, lp, lane, acc_rel, span); break;
+                    case 4: run_multi_store<4>(slots, nval, lp, lane, acc_rel, span); break;
+                    case 5: run_multi_store<5>(slots, nval, lp, lane, acc_rel, span); break;
+                    case 6: run_multi_store<6>(slots, nval, lp, lane, acc_rel, span); break;
+                    case 7: run_multi_store<7>(slots, nval, lp, lane, acc_rel, span); break;
+                    default: run_multi_store<8>(slots, nval, lp, lane, acc_rel, span); break;
+                    }
                 } else {
-                    for (int x0 = 0; x0 < span; x0 += 32) {
-                        if (x0 > 0) {
-                            // restage the masks of this pass (k and the offset stay)
-                            const int a = max(a0, x0) - x0, b = min(b0, x0 + 32) - x0;
-                            mask = 0u;
-                            if (b > a) mask = (0xffffffffu >> (32 - (b - a))) << a;
-                            __syncwarp();
-                            reinterpret_cast<int *>(&slots[pos])[3] = (int)mask;
-                            __syncwarp();
-                            if (!__any_sync(0xffffffffu, mask != 0u)) continue;
-                        }
+                    unsigned mask = 0u;
+                    {
+                        const int b = min(b0, 32);
+                        if (b > a0) mask = (0xffffffffu >> (32 - (b - a0))) << a0;
+                    }
+                    slots[pos] = make_double2(kval, __hiloint2double((int)mask, off));
+                    __syncwarp();
+                    if (span <= 8) {
                         const double acc =
-                            run_slots<32>(slots, nval, V.tprofile + x0 + lane, lane);
-                        const int x = lo_min + x0 + lane;
-                        if (x < hi_max) acc_tile[x - m0] += acc;
+                            run_slots<8>(slots, nval, V.tprofile + (lane & 7), lane);
+                        if (lane < 8 && lane < span) acc_rel[lane] += acc;
+                    } else if (span <= 16) {
+                        const double acc =
+                            run_slots<16>(slots, nval, V.tprofile + (lane & 15), lane);
+                        if (lane < 16 && lane < span) acc_rel[lane] += acc;
+                    } else {
+                        // generic: one pass of 32 outputs at a time with restaged lane masks
+                        for (int x0 = 0; x0 < span; x0 += 32) {
+                            if (x0 > 0) {
+                                const int a = max(a0, x0) - x0, b = min(b0, x0 + 32) - x0;
+                                mask = 0u;
+                                if (b > a) mask = (0xffffffffu >> (32 - (b - a))) << a;
+                                __syncwarp();
+                                reinterpret_cast<int *>(&slots[pos])[3] = (int)mask;
+                                __syncwarp();
+                                if (!__any_sync(0xffffffffu, mask != 0u)) continue;
+                            }
+                            const double acc =
+                                run_slots<32>(slots, nval, V.tprofile + x0 + lane, lane);
+                            if (x0 + lane < span) acc_rel[x0 + lane] += acc;
+                        }
                     }
                 }
                 __syncwarp();

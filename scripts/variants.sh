@@ -3,7 +3,6 @@ run() { # label, env...
   python -c "
 import json; d=json.load(open('gpurun_out/bv.json')); print('$1', d['ms_per_step'], d['detail']['strengths_ms'], d['detail']['accumulate_ms'], d['detail']['checksum'])"
 }
-PB200_ACC_KERNEL=owner run owner
 run chunk
 for k in 2 8; do PB200_KSPLIT=$k run chunk_ks$k; done
-for v in variant_c3 variant_cu4 variant_cu16 variant_c3u16; do PB200_LIB=$PWD/pyratbay_b200/$v.so run $v; done
+for v in $VARIANTS; do PB200_LIB=$PWD/pyratbay_b200/$v.so run $v; done
