@@ -182,6 +182,8 @@ struct pb200_engine {
     DevBuf<int> d_giown, d_gbin;
     DevBuf<unsigned int> d_gstart;
     DevBuf<unsigned short> d_giso;
+    DevBuf<int> d_multi;     // groups that absorbed lines (strengths pass B)
+    int nmulti = 0;
     int nbins = 0, binw = 1;
 
     // per-batch scratch (grown on demand)
@@ -338,6 +340,24 @@ int pb200_engine_set_grid(pb200_engine *e, const double *wn, int64_t nwave, cons
     PB_CUDA(cudaStreamSynchronize(e->stream));
     e->has_grid = true;
     e->has_lines = false;  // grouping depends on the fine grid
+    return 0;
+}
+
+// Static list of the co-add groups with more than one member (at most one per absorbed line).
+static int build_multi_list(pb200_engine *e) {
+    e->nmulti = 0;
+    if (e->ngroups == 0 || e->nadd == 0) return 0;
+    const size_t cap = (size_t)std::min<int64_t>(e->ngroups, e->nadd);
+    int rc = e->d_multi.alloc(cap + 1);  // last slot: the counter
+    if (rc) return rc;
+    unsigned int *count = reinterpret_cast<unsigned int *>(e->d_multi.p + cap);
+    rc = launch_multi_list(e->stream, e->d_gstart.p, e->ngroups, e->d_multi.p, count);
+    if (rc) return rc;
+    unsigned int n = 0;
+    PB_CUDA(cudaMemcpyAsync(&n, count, sizeof(n), cudaMemcpyDeviceToHost, e->stream));
+    PB_CUDA(cudaStreamSynchronize(e->stream));
+    e->nmulti = (int)n;
+    e->launches++;
     return 0;
 }
 
@@ -574,6 +594,8 @@ int pb200_engine_set_lines(pb200_engine *e, int64_t nlines, const double *wn,
             e->nadd = nadd_dev;
             e->nbins = nbins_all;
             e->binw = binw_all;
+            rc = build_multi_list(e);
+            if (rc) return rc;
             e->has_lines = true;
             return 0;
         }
@@ -663,6 +685,8 @@ int pb200_engine_set_lines(pb200_engine *e, int64_t nlines, const double *wn,
     e->nadd = nadd;
     e->nbins = nbins;
     e->binw = binw;
+    rc = build_multi_list(e);
+    if (rc) return rc;
     e->has_lines = true;
     return 0;
 }
@@ -993,9 +1017,9 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         PB_CUDA(cudaMemsetAsync(e->d_kmax.p, 0, sizeof(unsigned long long) * ntc * nrows, st));
         PB_CUDA(cudaEventRecord(e->ev[1], st));
         rc = launch_strengths(st, V, ntc, e->d_tp_temp.p, e->d_tp_isoz.p, e->d_iso_row.p, nrows,
-                              e->d_ksum.p, e->d_kmax.p);
+                              e->d_ksum.p, e->d_kmax.p, e->d_multi.p, e->nmulti);
         if (rc) return rc;
-        if (V.ngroups > 0) e->launches++;
+        if (V.ngroups > 0) e->launches += e->nmulti > 0 ? 2 : 1;
         PB_CUDA(cudaEventRecord(e->ev[2], st));
         // one launch per run of equal mode; grid.y is limited to 65535 units per launch
         for (size_t u0 = 0; u0 < cu.size();) {

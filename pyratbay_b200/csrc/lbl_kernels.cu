@@ -14,6 +14,9 @@
 // shared memory and then broadcast to the warp.
 #include "lbl_kernels.cuh"
 
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
 #include <algorithm>
 #include <climits>
 #include <cstdint>
@@ -107,6 +110,51 @@ __device__ __forceinline__ bool prepare_group(const StaticView &V, const UnitPar
 #ifndef PB200_STR_MINBLOCKS
 #define PB200_STR_MINBLOCKS 1
 #endif
+// SIGCTE*ratio*gf * exp(-EXPCTE*elow/T) * (1-exp(-EXPCTE*wn/T)) / Z   (_extcoeff.c:219-224)
+__device__ __forceinline__ double line_strength(const StaticView &V, unsigned int ln, double pref,
+                                                double temp, double z, double inv_t,
+                                                double inv_z) {
+    const double w = V.l_wn[ln];
+#if PB200_STR_RECIP
+    const double pop = exp(dmul(dmul(-kExpCte, V.l_elow[ln]), inv_t));
+    const double ind = dsub(1.0, exp(dmul(dmul(-kExpCte, w), inv_t)));
+    return dmul(dmul(dmul(dmul(pref, V.l_gf[ln]), pop), ind), inv_z);
+#else
+    const double pop = exp(ddiv(dmul(-kExpCte, V.l_elow[ln]), temp));
+    const double ind = dsub(1.0, exp(ddiv(dmul(-kExpCte, w), temp)));
+    return ddiv(dmul(dmul(dmul(pref, V.l_gf[ln]), pop), ind), z);
+#endif
+}
+
+// Fold the per-thread maxima of a 256-thread block into kmax.  kprop >= 0, so the IEEE bit
+// pattern orders like the value: warp maximum with two 32-bit REDUX (high words, then low words
+// among the lanes holding the largest high word), one atomic per block.  With several output
+// rows every thread with a positive value issues its own atomic (rare: add == 0, nspec > 1).
+__device__ __forceinline__ void block_max_to_kmax(double best, int row, int nrows, int tp,
+                                                  unsigned long long *__restrict__ kmax) {
+    if (nrows == 1) {
+        const unsigned hi = (unsigned)__double2hiint(best), lo = (unsigned)__double2loint(best);
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        __shared__ unsigned long long s_best[8];
+        if ((threadIdx.x & 31) == 0)
+            s_best[threadIdx.x >> 5] = ((unsigned long long)mh << 32) | ml;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long m = s_best[0];
+            for (int i = 1; i < 8; i++) m = s_best[i] > m ? s_best[i] : m;
+            if (m) atomicMax(&kmax[tp], m);
+        }
+    } else if (row >= 0 && best > 0.0) {
+        atomicMax(&kmax[(size_t)tp * nrows + row],
+                  (unsigned long long)__double_as_longlong(best));
+    }
+}
+
+// Pass A: one thread per group, HEAD line only (straight-line code: 98 % of the groups of a
+// 1e6-line list have a single member, and a loop over members makes every warp that holds one
+// longer group run the two exponentials again for all 32 lanes).  Pass B (below) redoes the
+// groups that absorbed lines.
 __global__ void __launch_bounds__(256, PB200_STR_MINBLOCKS)
 strengths_kernel(StaticView V, const double *__restrict__ tp_temp,
                  const double *__restrict__ tp_isoz, const int *__restrict__ iso_row,
@@ -124,44 +172,55 @@ strengths_kernel(StaticView V, const double *__restrict__ tp_temp,
             const double temp = tp_temp[tp];
             const double z = tp_isoz[(size_t)tp * V.niso + iso];
             const double pref = dmul(kSigCte, V.iso_ratio[iso]);
-            const unsigned int s = V.g_start[g], e = V.g_start[g + 1];
-#if PB200_STR_RECIP
             const double inv_t = ddiv(1.0, temp), inv_z = ddiv(1.0, z);
-#endif
-            for (unsigned int ln = s; ln < e; ln++) {
-                const double w = V.l_wn[ln];
-                // SIGCTE*ratio*gf * exp(-EXPCTE*elow/T) * (1-exp(-EXPCTE*wn/T)) / Z   (:219-224)
-#if PB200_STR_RECIP
-                const double pop = exp(dmul(dmul(-kExpCte, V.l_elow[ln]), inv_t));
-                const double ind = dsub(1.0, exp(dmul(dmul(-kExpCte, w), inv_t)));
-                const double kl = dmul(dmul(dmul(dmul(pref, V.l_gf[ln]), pop), ind), inv_z);
-#else
-                const double pop = exp(ddiv(dmul(-kExpCte, V.l_elow[ln]), temp));
-                const double ind = dsub(1.0, exp(ddiv(dmul(-kExpCte, w), temp)));
-                const double kl = ddiv(dmul(dmul(dmul(pref, V.l_gf[ln]), pop), ind), z);
-#endif
-                k = (ln == s) ? kl : dadd(k, kl);  // :248,258 sequential co-add
-                best = fmax(best, kl);             // :225 maximum over single lines
-            }
+            k = line_strength(V, V.g_start[g], pref, temp, z, inv_t, inv_z);
+            best = k;
         }
         ksum[(size_t)tp * V.ngroups + g] = k;
     }
-    // kprop >= 0, so the IEEE bit pattern orders like the value.
-    if (nrows == 1) {
-        for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
-        __shared__ double s_best[8];
-        if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int i = 1; i < 8; i++) best = fmax(best, s_best[i]);
-            if (best > 0.0)
-                atomicMax(&kmax[tp], (unsigned long long)__double_as_longlong(best));
-        }
-    } else if (row >= 0 && best > 0.0) {
-        atomicMax(&kmax[(size_t)tp * nrows + row],
-                  (unsigned long long)__double_as_longlong(best));
-    }
+    block_max_to_kmax(best, row, nrows, tp, kmax);
 }
+
+// Pass B: the groups with absorbed lines (static list built at set_lines): the reference's
+// sequential co-add k = k_head + k_1 + k_2 ... in member order (:248,258), and the maximum
+// over every single line (:225).
+__global__ void __launch_bounds__(256)
+strengths_multi_kernel(StaticView V, const int *__restrict__ multi, int nmulti,
+                       const double *__restrict__ tp_temp, const double *__restrict__ tp_isoz,
+                       const int *__restrict__ iso_row, int nrows, double *__restrict__ ksum,
+                       unsigned long long *__restrict__ kmax) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tp = blockIdx.y;
+    double best = 0.0;
+    int row = -1;
+    if (i < nmulti) {
+        const int g = multi[i];
+        const int iso = V.g_iso[g];
+        row = iso_row[iso];
+        if (row >= 0) {
+            const double temp = tp_temp[tp];
+            const double z = tp_isoz[(size_t)tp * V.niso + iso];
+            const double pref = dmul(kSigCte, V.iso_ratio[iso]);
+            const double inv_t = ddiv(1.0, temp), inv_z = ddiv(1.0, z);
+            const unsigned int s = V.g_start[g], e = V.g_start[g + 1];
+            double k = 0.0;
+            for (unsigned int ln = s; ln < e; ln++) {
+                const double kl = line_strength(V, ln, pref, temp, z, inv_t, inv_z);
+                k = (ln == s) ? kl : dadd(k, kl);
+                best = fmax(best, kl);
+            }
+            ksum[(size_t)tp * V.ngroups + g] = k;
+        }
+    }
+    block_max_to_kmax(best, row, nrows, tp, kmax);
+}
+
+// Static list of the groups that absorbed at least one line, in group order (ordered
+// compaction, so pass B reads its lines and writes ksum with ascending addresses).
+struct HasAbsorbed {
+    const unsigned int *g_start;
+    __device__ bool operator()(int g) const { return g_start[g + 1] - g_start[g] > 1u; }
+};
 
 // ---------------------------------------------------------------------------------------
 // Kernel 3: output-owned accumulation.  grid = (tiles, units, rows), 256 threads.
@@ -883,11 +942,33 @@ interp_ec_kernel(double *__restrict__ ext, const double *__restrict__ table,
 // Launch wrappers
 int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double *tp_temp,
                      const double *tp_isoz, const int *iso_row, int nrows, double *ksum,
-                     unsigned long long *kmax) {
+                     unsigned long long *kmax, const int *multi, int nmulti) {
     if (V.ngroups == 0 || ntp == 0) return 0;
     dim3 grid((unsigned)((V.ngroups + 255) / 256), (unsigned)ntp);
     strengths_kernel<<<grid, 256, 0, st>>>(V, tp_temp, tp_isoz, iso_row, nrows, ksum, kmax);
     PB_CUDA(cudaGetLastError());
+    if (nmulti > 0) {
+        dim3 mgrid((unsigned)((nmulti + 255) / 256), (unsigned)ntp);
+        strengths_multi_kernel<<<mgrid, 256, 0, st>>>(V, multi, nmulti, tp_temp, tp_isoz, iso_row,
+                                                     nrows, ksum, kmax);
+        PB_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int launch_multi_list(cudaStream_t st, const unsigned int *g_start, long long ngroups,
+                      int *multi, unsigned int *count) {
+    if (ngroups == 0) return 0;
+    thrust::counting_iterator<int> ids(0);
+    HasAbsorbed pred{g_start};
+    size_t tmp_bytes = 0;
+    PB_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, ids, multi, count, (int)ngroups, pred, st));
+    void *tmp = nullptr;
+    PB_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    cudaError_t err = cub::DeviceSelect::If(tmp, tmp_bytes, ids, multi, count, (int)ngroups, pred, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    if (err != cudaSuccess) return cuda_fail(err, "cub::DeviceSelect::If", __FILE__, __LINE__);
     return 0;
 }
 

@@ -6,7 +6,11 @@ namespace pb200 {
 
 int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double *tp_temp,
                      const double *tp_isoz, const int *iso_row, int nrows, double *ksum,
-                     unsigned long long *kmax);
+                     unsigned long long *kmax, const int *multi, int nmulti);
+
+// List the groups with more than one member line (set_lines; `count` must be zeroed).
+int launch_multi_list(cudaStream_t st, const unsigned int *g_start, long long ngroups,
+                      int *multi, unsigned int *count);
 
 int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
                       const UnitParams *units, const IsoUnit *iso_units, const int *iso_row,

@@ -113,7 +113,9 @@ class Line_By_Line:
                 # the reference multiplies by density[layer] (one entry per LBL species)
                 ec[i] *= dens[i] if len(dens) == self.nspec else dens
             return ec
-        self.ec[:] = 0.0
+        # The reference zeroes self.ec and lets the C code accumulate into it; the batched
+        # call overwrites every element of self.ec (zeros where nothing contributes), so the
+        # 8*nlayers*nwave-byte host memset is not needed.
         ex.extinction(self.pyrat, np.arange(self.nlayers), grid=False, add=True,
                       skip_mol=skip_mol)
         return self.ec
