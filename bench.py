@@ -157,7 +157,7 @@ def ncu_traffic(args):
     the default workload it was taken on."""
     default = (args.nlines == 1_000_000 and args.nlayers == 81 and args.wl_low == 0.5
                and args.wl_high == 5.0 and args.ptop == 1e-6 and args.pbottom == 100.0)
-    return 1.511902e9 + 48.091136e6 if default else None
+    return 1.498723e9 + 47.172096e6 if default else None
 
 
 def run_b200(args):
@@ -282,17 +282,18 @@ def run_b200(args):
     algo_bytes = 20.0 * neval + 8.0 * nlayers * nwave
     achieved = algo_bytes / (acc_ms * 1e-3) / 1e9
     fp64_tf, l2_gbs = device_ceilings(local_rank)
-    roofline = {"bound": "hbm", "kernel": "accumulate_kernel<kTransposed>",
+    roofline = {"bound": "hbm", "kernel": "accumulate_chunks_kernel",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": ncu_traffic(args),
-                "traffic_source": "profiles/r01e_accumulate_final.txt (ncu --set full, "
+                "traffic_source": "profiles/r01h_chunk_forward.txt (ncu --set full, "
                                   "dram__bytes_read+write of one launch; default workload only)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "voigt_table_first_touch_upper_bound_bytes": float(table_bytes),
                 "launch_ms": acc_ms, "share_of_step": acc_ms / ms_per_step,
-                "note": "the kernel is issue/LSU bound (DESIGN.md section 5), see roofline_l2 / "
-                        "roofline_fp64 for the other ceilings"}
+                "note": "HBM traffic equals the algorithmic bytes; the kernel is bound by the L1 "
+                        "data pipe and L2->SM bandwidth of the profile gathers (DESIGN.md "
+                        "section 5), see roofline_l2 / roofline_fp64 for those ceilings"}
     roofline_l2 = {"bound": "l2", "achieved": 8.0 * gathered / (acc_ms * 1e-3) / 1e9,
                    "peak": l2_gbs, "unit": "GB/s",
                    "frac": 8.0 * gathered / (acc_ms * 1e-3) / 1e9 / l2_gbs,

@@ -13,6 +13,10 @@ KEYS = [
     'lts__t_sectors_op_read.sum', 'lts__t_bytes.sum',
     'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__t_sector_hit_rate.pct',
     'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
+    'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+    'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+    'l1tex__lsu_writeback_active_mem_lgds.sum.pct_of_peak_sustained_elapsed',
+    'l1tex__m_xbar2l1tex_read_bytes.sum', 'lts__t_sectors_srcunit_tex_op_read.sum',
     'sm__throughput.avg.pct_of_peak_sustained_elapsed',
     'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
     'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
