@@ -1,5 +1,5 @@
 """Command-line entry: `python -m pyratbay_b200 -c opacity.cfg` (the `pbay -c` of the
-reference, pyratbay/__main__.py:11-127, restricted to runmode = opacity)."""
+reference, pyratbay/__main__.py:11-127, restricted to runmode = tli and runmode = opacity)."""
 import argparse
 import sys
 
@@ -10,7 +10,8 @@ from .pyrat import run
 def main():
     parser = argparse.ArgumentParser(
         prog="pyratbay_b200",
-        description="B200-native cross-section table builder (runmode = opacity).")
+        description="B200-native cross-section table builder (runmode = opacity) and TLI "
+                    "writer (runmode = tli).")
     parser.add_argument("-c", dest="cfile", required=True,
                         help="Pyrat Bay configuration file ([pyrat] section)")
     parser.add_argument("--device", type=int, default=0, help="CUDA device index")
@@ -18,9 +19,9 @@ def main():
                         version=f"pyratbay_b200 {__version__}")
     args = parser.parse_args()
     pyrat = run(args.cfile, device=args.device)
-    if pyrat.inputs.runmode != "opacity":
+    if pyrat is not None and pyrat.inputs.runmode != "opacity":
         sys.exit(f"runmode '{pyrat.inputs.runmode}' is outside the scope of pyratbay_b200 "
-                 "(only 'opacity' is implemented)")
+                 "(only 'tli' and 'opacity' are implemented)")
 
 
 if __name__ == "__main__":

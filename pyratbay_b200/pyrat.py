@@ -104,7 +104,20 @@ class Pyrat:
 
 
 def run(cfile, device=0):
-    """Driver for runmode=opacity (driver.py:59-61)."""
+    """Driver for runmode = tli (driver.py:35-46) and runmode = opacity (driver.py:59-61)."""
+    inputs = pt.parse(cfile)
+    if inputs.runmode == 'tli':
+        from . import constants as pc
+        from . import lread
+        log = pt.Log(inputs.logfile, verb=inputs.verb if inputs.verb is not None else 2)
+        if inputs.tlifile is None:
+            log.error('Undefined TLI file (tlifile)')
+        # wavelengths back to their original units, as the reference passes them
+        wl_low = inputs.wl_low / pc.u(inputs.wlunits) if inputs.wl_low is not None else None
+        wl_high = inputs.wl_high / pc.u(inputs.wlunits) if inputs.wl_high is not None else None
+        lread.make_tli(inputs.dblist, inputs.pflist, inputs.dbtype, inputs.tlifile[0],
+                       wl_low, wl_high, inputs.wlunits, log)
+        return None
     pyrat = Pyrat(cfile, device=device)
     if pyrat.inputs.runmode == 'opacity':
         pyrat.compute_opacity()

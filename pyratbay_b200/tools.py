@@ -139,6 +139,17 @@ def parse(cfile):
     if args.sampled_cs is None and args.runmode == 'opacity' and args.logfile:
         args.sampled_cs = [os.path.splitext(args.logfile)[0] + '.npz']  # parser.py:695-696
     root = os.path.dirname(os.path.abspath(cfile))
+    # runmode = tli (parser.py:456-460,709): databases, their types and partition functions
+    args.dblist = sec['dblist'].split() if 'dblist' in sec else None
+    args.dbtype = sec['dbtype'].split() if 'dbtype' in sec else None
+    args.pflist = sec['pflist'].split() if 'pflist' in sec else None
+    if args.dblist is not None:
+        args.dblist = [p if os.path.isabs(p) else os.path.join(root, p) for p in args.dblist]
+    if args.pflist is not None:
+        args.pflist = [p if (p in ('tips', 'poly') or os.path.isabs(p))
+                       else os.path.join(root, p) for p in args.pflist]
+    if args.tlifile is None and args.runmode == 'tli' and sec.get('logfile'):
+        args.tlifile = [os.path.splitext(sec.get('logfile'))[0] + '.tli']  # parser.py:693-694
     for key in ['logfile', 'atmfile']:
         v = getattr(args, key)
         if v is not None and not os.path.isabs(v):
