@@ -171,6 +171,37 @@ def _column_float(rec, lo, hi):
     return np.ascontiguousarray(rec[:, lo:hi]).view(f'S{hi - lo}').ravel().astype(np.double)
 
 
+def _first_three_fields(rec):
+    """(int, int, float) columns of fixed-format text records (ExoMol .trans: '%12d %12d
+    %10.4e ...').  The column boundaries are taken from the first record; when every record
+    has blanks exactly there the fields are converted column-wise, otherwise (ragged input)
+    record by record like the reference does."""
+    first = rec[0].tobytes()
+    spans, pos = [], 0
+    for _ in range(3):
+        while pos < len(first) and first[pos:pos + 1].isspace():
+            pos += 1
+        start = pos
+        while pos < len(first) and not first[pos:pos + 1].isspace():
+            pos += 1
+        spans.append((start, pos))
+    # field k occupies [previous field's end, its own end): right-aligned numbers
+    edges = [0] + [e for _, e in spans]
+    seps = [e for e in edges[1:] if e < rec.shape[1]]
+    blank = np.isin(rec[:, seps], (32, 9, 10, 13)).all() if seps else True
+    if blank and spans[2][1] > spans[2][0]:
+        cols = [np.ascontiguousarray(rec[:, edges[k]:edges[k + 1]])
+                .view(f'S{edges[k + 1] - edges[k]}').ravel() for k in range(3)]
+        try:
+            return cols[0].astype(np.int64), cols[1].astype(np.int64), cols[2].astype(np.double)
+        except ValueError:
+            pass  # a record with shifted columns: fall through to the generic split
+    fields = np.array([r.split(None, 3)[:3]
+                       for r in rec.view(f'S{rec.shape[1]}').ravel().tolist()])
+    return (fields[:, 0].astype(np.int64), fields[:, 1].astype(np.int64),
+            fields[:, 2].astype(np.double))
+
+
 class Hitran(Linelist):
     """HITRAN/HITEMP 160-character `.par` reader (linelist/hitran.py)."""
     rec_iso, rec_wn, rec_strength, rec_A21, rec_air = 2, 3, 15, 25, 35
@@ -263,11 +294,7 @@ class Exomol(Linelist):
         nlines = len(text) // self.recsize
         # upper id, lower id, A21: the first three fields of every (equal-length) record
         rec = np.frombuffer(text, np.uint8, nlines * self.recsize).reshape(nlines, self.recsize)
-        fields = np.array([r.split(None, 3)[:3] for r in
-                           rec.view(f'S{self.recsize}').ravel().tolist()])
-        up = fields[:, 0].astype(np.int64)
-        lo = fields[:, 1].astype(np.int64)
-        a21 = fields[:, 2].astype(np.double)
+        up, lo, a21 = _first_three_fields(rec)
         wn_all = self.E[up] - self.E[lo]
         window = self._window(wn_all, iwn, fwn)
         if window is None:
