@@ -182,8 +182,8 @@ struct pb200_engine {
     DevBuf<int> d_giown, d_gbin;
     DevBuf<unsigned int> d_gstart;
     DevBuf<unsigned short> d_giso;
-    DevBuf<int> d_multi;     // groups that absorbed lines (strengths pass B)
-    int nmulti = 0;
+    DevBuf<int> d_lgroup;    // co-add group of every in-window line (strengths kernel)
+    DevBuf<unsigned short> d_liso;
     int nbins = 0, binw = 1;
 
     // per-batch scratch (grown on demand)
@@ -343,20 +343,17 @@ int pb200_engine_set_grid(pb200_engine *e, const double *wn, int64_t nwave, cons
     return 0;
 }
 
-// Static list of the co-add groups with more than one member (at most one per absorbed line).
-static int build_multi_list(pb200_engine *e) {
-    e->nmulti = 0;
-    if (e->ngroups == 0 || e->nadd == 0) return 0;
-    const size_t cap = (size_t)std::min<int64_t>(e->ngroups, e->nadd);
-    int rc = e->d_multi.alloc(cap + 1);  // last slot: the counter
+// l_group[line] for the line-parallel strengths kernel.
+static int build_line_groups(pb200_engine *e) {
+    if (e->ngroups == 0 || e->n_inwin == 0) return 0;
+    int rc = e->d_lgroup.alloc((size_t)e->n_inwin);
     if (rc) return rc;
-    unsigned int *count = reinterpret_cast<unsigned int *>(e->d_multi.p + cap);
-    rc = launch_multi_list(e->stream, e->d_gstart.p, e->ngroups, e->d_multi.p, count);
+    if (!rc) rc = e->d_liso.alloc((size_t)e->n_inwin);
     if (rc) return rc;
-    unsigned int n = 0;
-    PB_CUDA(cudaMemcpyAsync(&n, count, sizeof(n), cudaMemcpyDeviceToHost, e->stream));
+    rc = launch_line_groups(e->stream, e->d_gstart.p, e->d_giso.p, e->ngroups, e->d_lgroup.p,
+                            e->d_liso.p);
+    if (rc) return rc;
     PB_CUDA(cudaStreamSynchronize(e->stream));
-    e->nmulti = (int)n;
     e->launches++;
     return 0;
 }
@@ -594,7 +591,7 @@ int pb200_engine_set_lines(pb200_engine *e, int64_t nlines, const double *wn,
             e->nadd = nadd_dev;
             e->nbins = nbins_all;
             e->binw = binw_all;
-            rc = build_multi_list(e);
+            rc = build_line_groups(e);
             if (rc) return rc;
             e->has_lines = true;
             return 0;
@@ -685,7 +682,7 @@ int pb200_engine_set_lines(pb200_engine *e, int64_t nlines, const double *wn,
     e->nadd = nadd;
     e->nbins = nbins;
     e->binw = binw;
-    rc = build_multi_list(e);
+    rc = build_line_groups(e);
     if (rc) return rc;
     e->has_lines = true;
     return 0;
@@ -895,6 +892,10 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         }
     }
     const int ntp = (int)tp_temp.size();
+    // the strengths kernel multiplies by 1/T and 1/Z (IEEE reciprocals taken here, once)
+    std::vector<double> tp_inv_t(tp_temp.size()), tp_inv_z(tp_isoz.size());
+    for (size_t i = 0; i < tp_temp.size(); i++) tp_inv_t[i] = 1.0 / tp_temp[i];
+    for (size_t i = 0; i < tp_isoz.size(); i++) tp_inv_z[i] = 1.0 / tp_isoz[i];
 
     // Accumulate mode per unit: constant-step outputs read the output-stride table when the
     // unit's dynamic stride ofactor*scale equals the table's stride (always true when
@@ -1006,9 +1007,9 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
                           iso_units.begin() + (size_t)(u + 1) * niso);
             }
         }
-        PB_CUDA(cudaMemcpyAsync(e->d_tp_temp.p, tp_temp.data() + tp0, sizeof(double) * ntc,
+        PB_CUDA(cudaMemcpyAsync(e->d_tp_temp.p, tp_inv_t.data() + tp0, sizeof(double) * ntc,
                                 cudaMemcpyHostToDevice, st));
-        PB_CUDA(cudaMemcpyAsync(e->d_tp_isoz.p, tp_isoz.data() + (size_t)tp0 * niso,
+        PB_CUDA(cudaMemcpyAsync(e->d_tp_isoz.p, tp_inv_z.data() + (size_t)tp0 * niso,
                                 sizeof(double) * ntc * niso, cudaMemcpyHostToDevice, st));
         PB_CUDA(cudaMemcpyAsync(e->d_units.p, cu.data(), sizeof(UnitParams) * cu.size(),
                                 cudaMemcpyHostToDevice, st));
@@ -1017,9 +1018,9 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         PB_CUDA(cudaMemsetAsync(e->d_kmax.p, 0, sizeof(unsigned long long) * ntc * nrows, st));
         PB_CUDA(cudaEventRecord(e->ev[1], st));
         rc = launch_strengths(st, V, ntc, e->d_tp_temp.p, e->d_tp_isoz.p, e->d_iso_row.p, nrows,
-                              e->d_ksum.p, e->d_kmax.p, e->d_multi.p, e->nmulti);
+                              e->d_ksum.p, e->d_kmax.p, e->d_lgroup.p, e->d_liso.p, e->n_inwin);
         if (rc) return rc;
-        if (V.ngroups > 0) e->launches += e->nmulti > 0 ? 2 : 1;
+        if (V.ngroups > 0) e->launches++;
         PB_CUDA(cudaEventRecord(e->ev[2], st));
         // one launch per run of equal mode; grid.y is limited to 65535 units per launch
         for (size_t u0 = 0; u0 < cu.size();) {

@@ -14,8 +14,6 @@
 // shared memory and then broadcast to the warp.
 #include "lbl_kernels.cuh"
 
-#include <cub/device/device_select.cuh>
-#include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
 #include <climits>
@@ -108,119 +106,117 @@ __device__ __forceinline__ bool prepare_group(const StaticView &V, const UnitPar
 #define PB200_STR_RECIP 1
 #endif
 #ifndef PB200_STR_MINBLOCKS
-#define PB200_STR_MINBLOCKS 1
+#define PB200_STR_MINBLOCKS 4
 #endif
 // SIGCTE*ratio*gf * exp(-EXPCTE*elow/T) * (1-exp(-EXPCTE*wn/T)) / Z   (_extcoeff.c:219-224)
-__device__ __forceinline__ double line_strength(const StaticView &V, unsigned int ln, double pref,
-                                                double temp, double z, double inv_t,
-                                                double inv_z) {
-    const double w = V.l_wn[ln];
-#if PB200_STR_RECIP
-    const double pop = exp(dmul(dmul(-kExpCte, V.l_elow[ln]), inv_t));
+// with the divisions by T and Z as multiplications by the host-rounded reciprocals.
+__device__ __forceinline__ double line_strength(double w, double elow, double gf, double pref,
+                                                double inv_t, double inv_z) {
+    const double pop = exp(dmul(dmul(-kExpCte, elow), inv_t));
     const double ind = dsub(1.0, exp(dmul(dmul(-kExpCte, w), inv_t)));
-    return dmul(dmul(dmul(dmul(pref, V.l_gf[ln]), pop), ind), inv_z);
-#else
-    const double pop = exp(ddiv(dmul(-kExpCte, V.l_elow[ln]), temp));
-    const double ind = dsub(1.0, exp(ddiv(dmul(-kExpCte, w), temp)));
-    return ddiv(dmul(dmul(dmul(pref, V.l_gf[ln]), pop), ind), z);
-#endif
+    return dmul(dmul(dmul(dmul(pref, gf), pop), ind), inv_z);
 }
 
-// Fold the per-thread maxima of a 256-thread block into kmax.  kprop >= 0, so the IEEE bit
-// pattern orders like the value: warp maximum with two 32-bit REDUX (high words, then low words
-// among the lanes holding the largest high word), one atomic per block.  With several output
-// rows every thread with a positive value issues its own atomic (rare: add == 0, nspec > 1).
-__device__ __forceinline__ void block_max_to_kmax(double best, int row, int nrows, int tp,
-                                                  unsigned long long *__restrict__ kmax) {
-    if (nrows == 1) {
-        const unsigned hi = (unsigned)__double2hiint(best), lo = (unsigned)__double2loint(best);
-        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
-        __shared__ unsigned long long s_best[8];
-        if ((threadIdx.x & 31) == 0)
-            s_best[threadIdx.x >> 5] = ((unsigned long long)mh << 32) | ml;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long m = s_best[0];
-            for (int i = 1; i < 8; i++) m = s_best[i] > m ? s_best[i] : m;
-            if (m) atomicMax(&kmax[tp], m);
-        }
-    } else if (row >= 0 && best > 0.0) {
-        atomicMax(&kmax[(size_t)tp * nrows + row],
-                  (unsigned long long)__double_as_longlong(best));
-    }
-}
+// Kernel 1.  One thread per in-window LINE, kStrTemps temperature passes per thread:
+//  * every line strength is evaluated exactly once whatever the co-add group sizes are (a
+//    per-group loop makes all 32 lanes of a warp redo the two exponentials as often as its
+//    longest group has members);
+//  * a line's wn/elow/gf, group code and isotope are independent coalesced loads issued once
+//    and reused for all the thread's temperatures (30 B per line instead of per line x T);
+//  * no block barrier: the members of a co-add group are adjacent lines, so the head lane
+//    collects them with shuffles in the reference's order k = k_head + k_1 + k_2 ... (:248,
+//    258); members that fall into the next warp are evaluated by the head lane itself.
+// l_group[line] = group id for a head line, ~group id (negative) for an absorbed member.
+// The maximum is taken over every single line (:225): warp REDUX of the IEEE bit pattern
+// (kprop >= 0 orders like its bits), one atomic per warp and pass, skipped when the running
+// maximum is already larger.
+constexpr int kStrTemps = 8;
 
-// Pass A: one thread per group, HEAD line only (straight-line code: 98 % of the groups of a
-// 1e6-line list have a single member, and a loop over members makes every warp that holds one
-// longer group run the two exponentials again for all 32 lanes).  Pass B (below) redoes the
-// groups that absorbed lines.
 __global__ void __launch_bounds__(256, PB200_STR_MINBLOCKS)
-strengths_kernel(StaticView V, const double *__restrict__ tp_temp,
-                 const double *__restrict__ tp_isoz, const int *__restrict__ iso_row,
-                 int nrows, double *__restrict__ ksum,
+strengths_kernel(StaticView V, const int *__restrict__ l_group,
+                 const unsigned short *__restrict__ l_iso, long long nlines, int ntp,
+                 const double *__restrict__ tp_inv_t, const double *__restrict__ tp_inv_z,
+                 const int *__restrict__ iso_row, int nrows, double *__restrict__ ksum,
                  unsigned long long *__restrict__ kmax) {
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int tp = blockIdx.y;
-    double best = 0.0;
-    int row = -1;
-    if (g < V.ngroups) {
-        const int iso = V.g_iso[g];
+    const long long ln = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long warp_end = ln - lane + 32;  // first line of the next warp
+    double w = 0.0, elow = 0.0, gf = 0.0, pref = 0.0;
+    int row = -1, code = INT_MIN, iso = 0;      // INT_MIN: past the end (acts like a head)
+    if (ln < nlines) {
+        w = V.l_wn[ln];
+        elow = V.l_elow[ln];
+        gf = V.l_gf[ln];
+        code = l_group[ln];
+        iso = l_iso[ln];
         row = iso_row[iso];
-        double k = 0.0;
-        if (row >= 0) {
-            const double temp = tp_temp[tp];
-            const double z = tp_isoz[(size_t)tp * V.niso + iso];
-            const double pref = dmul(kSigCte, V.iso_ratio[iso]);
-            const double inv_t = ddiv(1.0, temp), inv_z = ddiv(1.0, z);
-            k = line_strength(V, V.g_start[g], pref, temp, z, inv_t, inv_z);
-            best = k;
-        }
-        ksum[(size_t)tp * V.ngroups + g] = k;
+        if (row >= 0) pref = dmul(kSigCte, V.iso_ratio[iso]);
     }
-    block_max_to_kmax(best, row, nrows, tp, kmax);
+    // static group geometry inside the warp
+    const bool head = code >= 0;
+    const unsigned heads = __ballot_sync(0xffffffffu, code >= 0 || code == INT_MIN);
+    int nmem = 0;            // members of this head that sit in the following lanes
+    unsigned int ext_end = 0;  // one past the group's last line if it runs into the next warp
+    if (head) {
+        const unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
+        nmem = above ? __ffs(above) - 1 : 31 - lane;
+        if (!above && row >= 0) ext_end = V.g_start[code + 1];
+    }
+    const int maxm = __reduce_max_sync(0xffffffffu, (head && row >= 0) ? nmem : 0);
+
+    const int t0 = blockIdx.y * kStrTemps, t1 = min(ntp, t0 + kStrTemps);
+    unsigned long long mine = 0ull;  // lane j keeps the warp maximum of pass t0 + j
+    double nx_inv_t = tp_inv_t[t0], nx_inv_z = tp_inv_z[(size_t)t0 * V.niso + iso];
+#pragma unroll 1
+    for (int tp = t0; tp < t1; tp++) {
+        const double inv_t = nx_inv_t, inv_z = nx_inv_z;
+        if (tp + 1 < t1) {  // next pass's scalars, requested one pass ahead
+            nx_inv_t = tp_inv_t[tp + 1];
+            nx_inv_z = tp_inv_z[(size_t)(tp + 1) * V.niso + iso];
+        }
+        const double kl = row >= 0 ? line_strength(w, elow, gf, pref, inv_t, inv_z) : 0.0;
+        double k = kl;
+        for (int jm = 1; jm <= maxm; jm++) {
+            const double v = __shfl_down_sync(0xffffffffu, kl, jm);
+            if (jm <= nmem) k = dadd(k, v);
+        }
+        if (head) {
+            for (long long m = warp_end; m < (long long)ext_end; m++)
+                k = dadd(k, line_strength(V.l_wn[m], V.l_elow[m], V.l_gf[m], pref, inv_t, inv_z));
+            ksum[(size_t)tp * V.ngroups + code] = k;
+        }
+        if (nrows == 1) {
+            const unsigned hi = (unsigned)__double2hiint(kl), lo = (unsigned)__double2loint(kl);
+            const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+            if (lane == tp - t0) mine = ((unsigned long long)mh << 32) | ml;
+        } else if (row >= 0 && kl > 0.0) {
+            atomicMax(&kmax[(size_t)tp * nrows + row],
+                      (unsigned long long)__double_as_longlong(kl));
+        }
+    }
+    // one atomic per warp and pass, skipped when the running maximum is already larger; lane j
+    // handles pass t0 + j, after the arithmetic, so nothing in the loop waits on these reads
+    if (nrows == 1 && lane < t1 - t0) {
+        if (mine > *(volatile unsigned long long *)&kmax[t0 + lane])
+            atomicMax(&kmax[t0 + lane], mine);
+    }
 }
 
-// Pass B: the groups with absorbed lines (static list built at set_lines): the reference's
-// sequential co-add k = k_head + k_1 + k_2 ... in member order (:248,258), and the maximum
-// over every single line (:225).
+// l_group / l_iso of every in-window line (static; set_lines).
 __global__ void __launch_bounds__(256)
-strengths_multi_kernel(StaticView V, const int *__restrict__ multi, int nmulti,
-                       const double *__restrict__ tp_temp, const double *__restrict__ tp_isoz,
-                       const int *__restrict__ iso_row, int nrows, double *__restrict__ ksum,
-                       unsigned long long *__restrict__ kmax) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int tp = blockIdx.y;
-    double best = 0.0;
-    int row = -1;
-    if (i < nmulti) {
-        const int g = multi[i];
-        const int iso = V.g_iso[g];
-        row = iso_row[iso];
-        if (row >= 0) {
-            const double temp = tp_temp[tp];
-            const double z = tp_isoz[(size_t)tp * V.niso + iso];
-            const double pref = dmul(kSigCte, V.iso_ratio[iso]);
-            const double inv_t = ddiv(1.0, temp), inv_z = ddiv(1.0, z);
-            const unsigned int s = V.g_start[g], e = V.g_start[g + 1];
-            double k = 0.0;
-            for (unsigned int ln = s; ln < e; ln++) {
-                const double kl = line_strength(V, ln, pref, temp, z, inv_t, inv_z);
-                k = (ln == s) ? kl : dadd(k, kl);
-                best = fmax(best, kl);
-            }
-            ksum[(size_t)tp * V.ngroups + g] = k;
-        }
+line_group_kernel(const unsigned int *__restrict__ g_start,
+                  const unsigned short *__restrict__ g_iso, long long ngroups,
+                  int *__restrict__ l_group, unsigned short *__restrict__ l_iso) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    const unsigned int s = g_start[g], e = g_start[g + 1];
+    const unsigned short iso = g_iso[g];
+    for (unsigned int ln = s; ln < e; ln++) {
+        l_group[ln] = ln == s ? (int)g : ~(int)g;
+        l_iso[ln] = iso;
     }
-    block_max_to_kmax(best, row, nrows, tp, kmax);
 }
-
-// Static list of the groups that absorbed at least one line, in group order (ordered
-// compaction, so pass B reads its lines and writes ksum with ascending addresses).
-struct HasAbsorbed {
-    const unsigned int *g_start;
-    __device__ bool operator()(int g) const { return g_start[g + 1] - g_start[g] > 1u; }
-};
 
 // ---------------------------------------------------------------------------------------
 // Kernel 3: output-owned accumulation.  grid = (tiles, units, rows), 256 threads.
@@ -700,7 +696,10 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                 const int npass = (span + 31) >> 5;
                 // slot-major form: every group starts in pass 0 and ends in the last pass
                 const int bl = b0 - 32 * (npass - 1);
-                const bool multi = span > 16 && npass <= 8 &&
+#ifndef PB200_MULTI_MIN_SPAN
+#define PB200_MULTI_MIN_SPAN 32   // single-pass chunks: one LOP3 mask test (6 instr/slot vs 9)
+#endif
+                const bool multi = span > PB200_MULTI_MIN_SPAN && npass <= 8 &&
                                    __all_sync(0xffffffffu, !valid || (a0 < 32 && bl >= 1));
                 if (multi) {
                     slots[pos] = make_double2(
@@ -940,35 +939,25 @@ interp_ec_kernel(double *__restrict__ ext, const double *__restrict__ table,
 
 // ---------------------------------------------------------------------------------------
 // Launch wrappers
-int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double *tp_temp,
-                     const double *tp_isoz, const int *iso_row, int nrows, double *ksum,
-                     unsigned long long *kmax, const int *multi, int nmulti) {
-    if (V.ngroups == 0 || ntp == 0) return 0;
-    dim3 grid((unsigned)((V.ngroups + 255) / 256), (unsigned)ntp);
-    strengths_kernel<<<grid, 256, 0, st>>>(V, tp_temp, tp_isoz, iso_row, nrows, ksum, kmax);
+int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double *tp_inv_t,
+                     const double *tp_inv_z, const int *iso_row, int nrows, double *ksum,
+                     unsigned long long *kmax, const int *l_group,
+                     const unsigned short *l_iso, long long nlines) {
+    if (V.ngroups == 0 || ntp == 0 || nlines == 0) return 0;
+    dim3 grid((unsigned)((nlines + 255) / 256), (unsigned)((ntp + kStrTemps - 1) / kStrTemps));
+    strengths_kernel<<<grid, 256, 0, st>>>(V, l_group, l_iso, nlines, ntp, tp_inv_t, tp_inv_z,
+                                           iso_row, nrows, ksum, kmax);
     PB_CUDA(cudaGetLastError());
-    if (nmulti > 0) {
-        dim3 mgrid((unsigned)((nmulti + 255) / 256), (unsigned)ntp);
-        strengths_multi_kernel<<<mgrid, 256, 0, st>>>(V, multi, nmulti, tp_temp, tp_isoz, iso_row,
-                                                     nrows, ksum, kmax);
-        PB_CUDA(cudaGetLastError());
-    }
     return 0;
 }
 
-int launch_multi_list(cudaStream_t st, const unsigned int *g_start, long long ngroups,
-                      int *multi, unsigned int *count) {
+int launch_line_groups(cudaStream_t st, const unsigned int *g_start,
+                       const unsigned short *g_iso, long long ngroups, int *l_group,
+                       unsigned short *l_iso) {
     if (ngroups == 0) return 0;
-    thrust::counting_iterator<int> ids(0);
-    HasAbsorbed pred{g_start};
-    size_t tmp_bytes = 0;
-    PB_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, ids, multi, count, (int)ngroups, pred, st));
-    void *tmp = nullptr;
-    PB_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
-    cudaError_t err = cub::DeviceSelect::If(tmp, tmp_bytes, ids, multi, count, (int)ngroups, pred, st);
-    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
-    cudaFree(tmp);
-    if (err != cudaSuccess) return cuda_fail(err, "cub::DeviceSelect::If", __FILE__, __LINE__);
+    line_group_kernel<<<(unsigned)((ngroups + 255) / 256), 256, 0, st>>>(g_start, g_iso, ngroups,
+                                                                         l_group, l_iso);
+    PB_CUDA(cudaGetLastError());
     return 0;
 }
 

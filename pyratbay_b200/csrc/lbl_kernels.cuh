@@ -4,13 +4,16 @@
 
 namespace pb200 {
 
-int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double *tp_temp,
-                     const double *tp_isoz, const int *iso_row, int nrows, double *ksum,
-                     unsigned long long *kmax, const int *multi, int nmulti);
+// tp_inv_t[ntp] = 1/T and tp_inv_z[ntp, niso] = 1/Z of every strengths pass (host-rounded).
+int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double *tp_inv_t,
+                     const double *tp_inv_z, const int *iso_row, int nrows, double *ksum,
+                     unsigned long long *kmax, const int *l_group,
+                     const unsigned short *l_iso, long long nlines);
 
-// List the groups with more than one member line (set_lines; `count` must be zeroed).
-int launch_multi_list(cudaStream_t st, const unsigned int *g_start, long long ngroups,
-                      int *multi, unsigned int *count);
+// l_group[line] (group id for head lines, ~id for absorbed members) and l_iso[line]; set_lines.
+int launch_line_groups(cudaStream_t st, const unsigned int *g_start,
+                       const unsigned short *g_iso, long long ngroups, int *l_group,
+                       unsigned short *l_iso);
 
 int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
                       const UnitParams *units, const IsoUnit *iso_units, const int *iso_row,
