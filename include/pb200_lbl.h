@@ -155,6 +155,19 @@ void *pb200_engine_stream(const pb200_engine *e);
 int pb200_bench_fp64(int device, int reps, double *tflops);
 int pb200_bench_l2(int device, int mbytes, int reps, double *gbs);
 
+/* Exactness aids of the accumulate kernel (tests only).
+ * pb200_nearest_thresholds (host, no device needed): thr[j] = smallest double v whose nearest
+ * sample of the strictly increasing positive grid[n] is >= j (thr[0] = 0), the table that replaces
+ * the nearest-index search of _extcoeff.c:278 (pyramidsearch, utils.h:44-72); returns
+ * PB200_EINVAL when the grid is not strictly increasing (the engine then keeps the search).
+ * pb200_selftest_exact (device): draws n operands; mismatches[0] counts quotients a/b for which
+ * the FMA-only form used for idwn (_extcoeff.c:275) differs from the IEEE division,
+ * mismatches[1] the widths for which the threshold table and the bisection disagree. */
+int pb200_nearest_thresholds(const double *grid, int n, double *thr);
+int pb200_selftest_exact(int device, int64_t n, uint64_t seed, const double *steps, int nsteps,
+                         const double *grid, const double *thr, int ngrid,
+                         uint64_t mismatches[2]);
+
 /* Cross-section table interpolation in temperature ------------------------------------------
  * ext[nlayers,nwave] (or [nspec,nlayers,nwave] for per_mol) is ACCUMULATED (+=) like the
  * reference.  etable[nspec,ntemp,nlayers,nwave], ttable[ntemp], temperature[nlayers],

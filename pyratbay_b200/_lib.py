@@ -24,6 +24,7 @@ EXPORTS = [
     "pb200_extinction_batch_dev", "pb200_engine_last_timing", "pb200_engine_launch_count",
     "pb200_interp_ec", "pb200_interp_ec_per_mol", "pb200_interp_ec_dev",
     "pb200_engine_stream", "pb200_bench_fp64", "pb200_bench_l2",
+    "pb200_nearest_thresholds", "pb200_selftest_exact",
     "pb200_optical_depth", "pb200_optical_depth_dev",
 ]
 

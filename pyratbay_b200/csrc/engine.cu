@@ -688,6 +688,15 @@ int pb200_engine_set_lines(pb200_engine *e, int64_t nlines, const double *wn,
     return 0;
 }
 
+int pb200_nearest_thresholds(const double *grid, int n, double *thr) {
+    if (!grid || !thr || n < 1) return fail(PB200_EINVAL, "pb200_nearest_thresholds: null argument");
+    const std::vector<double> t = nearest_thresholds(grid, n);
+    if (t.empty()) return fail(PB200_EINVAL, "pb200_nearest_thresholds: grid must be positive and "
+                                             "strictly increasing with at least two samples");
+    std::copy(t.begin(), t.end(), thr);
+    return 0;
+}
+
 int pb200_engine_line_stats(const pb200_engine *e, int64_t stats[3]) {
     if (!e || !stats) return fail(PB200_EINVAL, "pb200_engine_line_stats: null argument");
     if (!e->has_lines) return fail(PB200_ESTATE, "pb200_engine_line_stats: no lines loaded");

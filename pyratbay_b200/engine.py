@@ -255,3 +255,26 @@ def device_ceilings(device=0, l2_mbytes=32, reps=3):
     check(lib.pb200_bench_l2(ctypes.c_int(device), ctypes.c_int(l2_mbytes), ctypes.c_int(reps),
                              ctypes.byref(gb)))
     return tf.value, gb.value
+
+
+def nearest_thresholds(grid):
+    """thr[j] = smallest double whose nearest sample of the increasing `grid` is >= j
+    (pb200_nearest_thresholds; host only)."""
+    g = _f64(grid)
+    thr = np.zeros(len(g), np.float64)
+    check(_lib.load().pb200_nearest_thresholds(_dp(g), ctypes.c_int(len(g)), _dp(thr)))
+    return thr
+
+
+def selftest_exact(steps, grid, n=1 << 24, seed=1, device=0):
+    """(quotient mismatches, nearest-index mismatches) of the device self-test
+    (pb200_selftest_exact): both must be zero."""
+    lib = _lib.load()
+    _lib.require_device()
+    s, g = _f64(steps), _f64(grid)
+    thr = nearest_thresholds(g)
+    bad = (ctypes.c_uint64 * 2)(0, 0)
+    check(lib.pb200_selftest_exact(
+        ctypes.c_int(device), ctypes.c_int64(int(n)), ctypes.c_uint64(int(seed)), _dp(s),
+        ctypes.c_int(len(s)), _dp(g), _dp(thr), ctypes.c_int(len(g)), bad))
+    return int(bad[0]), int(bad[1])

@@ -179,6 +179,7 @@ def test_forward_model_matches_reference():
     dict(nlines=200000, wnosamp=120),                  # dense: heavy co-adding
     dict(wnstep=0.25, wnosamp=360, wnlow=9000.0, wnhigh=9060.0),
     dict(nlines=300, wnlow=9000.0, wnhigh=9600.0),     # sparse: chunks span many outputs
+    dict(nlines=4000, wnstep=0.1, wnosamp=240, wnlow=9000.0, wnhigh=9030.0),  # > 8 passes/line
 ])
 @pytest.mark.parametrize("acc_mode", ["auto", "owner", "strided"])
 def test_extinction_matches_oracle_synthetic(kwargs, acc_mode, monkeypatch):
@@ -605,3 +606,20 @@ def test_device_line_preprocessing_edge_cases(monkeypatch):
     assert out["host"][0] == out["device"][0]
     assert np.array_equal(out["host"][1][0], out["device"][1][0])
     assert np.array_equal(out["host"][1][1], out["device"][1][1])
+
+
+def test_exact_quotient_and_threshold_index_selftest():
+    """The two exactness shortcuts of the accumulate kernel's prepare step (csrc/common.cuh):
+    idwn = (int)((wn - own0)/dwnstep) (_extcoeff.c:275) from a host-rounded reciprocal with
+    FMA corrections must equal the IEEE division bit for bit, and the Doppler threshold table
+    must give the index of the reference's nearest-sample search (:278) for every width --
+    including widths exactly on and one ulp below a threshold."""
+    from pyratbay_b200.engine import selftest_exact
+    from pyratbay_b200.spectrum import Spectrum
+    spec = Spectrum(wnlow=2000.0, wnhigh=20000.0, wnstep=1.0, wnosamp=2160)
+    steps = spec.ownstep * np.asarray(spec.odivisors, float)
+    steps = np.concatenate([steps, [1.0 / 2520, 0.25 / 360, 1.0 / 3, 1e-3 * (1 + 2.0**-52)]])
+    doppler = np.logspace(np.log10(2.3e-3), np.log10(0.27), 50)
+    for seed in (1, 2):
+        bad_q, bad_i = selftest_exact(steps, doppler, n=1 << 25, seed=seed)
+        assert bad_q == 0 and bad_i == 0

@@ -321,3 +321,24 @@ def test_str_of_voigt_and_line_by_line_match_reference():
     lbl = Line_By_Line(case.tlifile, case.atm.species, case.spec.wnlow, case.spec.wnhigh, fake)
     want = str(helpers.golden("mock_forward.npz")["lbl_str"])
     assert str(lbl).replace(str(lbl.tlifile), "['TLI']") == want
+
+
+def test_nearest_thresholds_reproduce_the_nearest_sample_search():
+    """pb200_nearest_thresholds (host): counting thresholds <= v equals the reference's
+    nearest-sample search with ties to the lower index (utils.h:44-72, 75-89)."""
+    from pyratbay_b200.engine import nearest_thresholds
+    from pyratbay_b200._lib import PB200Error
+    rng = np.random.default_rng(3)
+    for grid in (np.logspace(-3, 0, 40), np.array([1.0, 2.0, 2.5, 7.0]), np.linspace(0.1, 5, 17)):
+        thr = nearest_thresholds(grid)
+        assert thr[0] == 0.0 and np.all(np.diff(thr) > 0)
+        v = np.concatenate([rng.uniform(0, grid[-1] * 1.3, 20000), grid, thr[1:],
+                            np.nextafter(thr[1:], 0), 0.5 * (grid[1:] + grid[:-1])])
+        got = np.searchsorted(thr, v, side="right") - 1
+        hi = np.clip(np.searchsorted(grid, v, side="left"), 1, len(grid) - 1)
+        lo = hi - 1
+        want = np.where(np.abs(grid[hi] - v) < np.abs(grid[lo] - v), hi, lo)
+        want = np.where(v < grid[0], 0, np.where(v > grid[-1], len(grid) - 1, want))
+        assert np.array_equal(got, want)
+    with pytest.raises(PB200Error):
+        nearest_thresholds(np.array([1.0, 1.0, 2.0]))
