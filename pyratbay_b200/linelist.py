@@ -93,14 +93,16 @@ class Linelist:
 
     def getpf(self, verbose=0):
         """(temp, pf[niso, ntemp], isotope names) (driver.py:17-62).  'tips' is served from
-        the bundled TIPS-2021 H2O table; other molecules need a tabulated file."""
+        the bundled TIPS-2021 tables (data/tips_subset.npz: H2O, CO2, CO, CH4, NH3, HCN); other
+        molecules need a tabulated file."""
         if self.pffile == 'tips':
-            if self.molecule != 'H2O':
-                self.log.error(
-                    f"pflist = tips: no bundled TIPS table for {self.molecule}; give a "
-                    "partition-function file instead")
-            temp, z = ptli.h2o_partition_table()
-            return temp, z, list(ptli.H2O_ISOTOPES['names'])
+            with np.load(os.path.join(_DATA, 'tips_subset.npz')) as tips:
+                if f'{self.molecule}_z' not in tips:
+                    self.log.error(
+                        f"pflist = tips: no bundled TIPS table for {self.molecule}; give a "
+                        "partition-function file instead")
+                return (tips[f'{self.molecule}_temp'].copy(), tips[f'{self.molecule}_z'].copy(),
+                        [str(i) for i in tips[f'{self.molecule}_iso']])
         pf, iso, temp = read_pf(self.pffile)
         return temp, pf, iso.tolist()
 

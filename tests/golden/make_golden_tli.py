@@ -13,6 +13,9 @@ modules as make_golden.py.  Writes:
   pyratbay_b200/data/isotopes_subset.json
                                    isotope names / ratios / masses and HITRAN order of the
                                    molecules of the benchmark configs (from the reference's data)
+  pyratbay_b200/data/tips_subset.npz
+                                   TIPS-2021 partition functions of the same molecules
+  tests/golden/repack_co2_tips.tli reference TLI of the repack CO2 list with pflist = tips
 (mock_hitran_h2o.tli with pflist=tips comes from make_golden.py.)
 """
 import json
@@ -107,6 +110,28 @@ verb = 1
         }
     with open(os.path.join(REPO, "pyratbay_b200", "data", "isotopes_subset.json"), "w") as f:
         json.dump(data, f, indent=1)
+
+    # TIPS-2021 partition functions of the same molecules (pflist = tips)
+    tables = {}
+    for name in MOLECULES:
+        z, iso, temp = pf.tips(name)
+        tables[f"{name}_temp"] = np.asarray(temp, np.double)
+        tables[f"{name}_z"] = np.asarray(z, np.double)
+        tables[f"{name}_iso"] = np.array([str(i) for i in iso])
+    np.savez_compressed(os.path.join(REPO, "pyratbay_b200", "data", "tips_subset.npz"), **tables)
+
+    # HITRAN CO2 with pflist = tips through the reference (golden for the bundled table)
+    write_cfg("repack_tips.cfg", """runmode = tli
+logfile = outputs/repack_co2_tips.log
+dblist = inputs/CO2_hitran_2.50-2.52um_repack-0.01_lbl.dat
+dbtype = repack
+pflist = tips
+wl_low  = 2.50 um
+wl_high = 2.52 um
+verb = 1
+""")
+    pb.run("repack_tips.cfg")
+    shutil.copy("outputs/repack_co2_tips.tli", os.path.join(HERE, "repack_co2_tips.tli"))
     print("done")
 
 

@@ -116,3 +116,11 @@ verb = 0
 """)
     assert pb.run(str(cfg)) is None
     assert _same_file(str(tmp_path / "ExoMol_NH3.tli"), os.path.join(GOLD, "exomol_nh3.tli"))
+
+
+def test_bundled_tips_tables(tmp_path):
+    """pflist = tips for a molecule other than H2O: TLI byte-identical to the reference's."""
+    out = str(tmp_path / "co2_tips.tli")
+    lread.make_tli(os.path.join(INP, "CO2_hitran_2.50-2.52um_repack-0.01_lbl.dat"), "tips",
+                   "repack", out, 2.50, 2.52, "um")
+    assert _same_file(out, os.path.join(GOLD, "repack_co2_tips.tli"))
