@@ -29,14 +29,25 @@ class Line_By_Line:
         self.ec = pinned_zeros((self.nlayers, self.nwave))
 
         # Collect all databases; isotope ids are offset per *file* (line_by_line.py:112-125)
+        # (one concatenation at the end, none for a single file: at 1e8 lines every avoidable
+        # copy of a column is 0.8 GB)
+        cols = {'wn': [], 'gf': [], 'elow': [], 'isoid': []}
         for tli_file in self.tlifile:
             databases, wn, gf, elow, iso_id = read_tli_file(tli_file, wn_low, wn_high, log)
             niso = int(np.sum([db.niso for db in self.db]))
-            self.isoid = np.concatenate((self.isoid, iso_id.astype(int) + niso))
+            iso_id = iso_id.astype(int)
+            if niso:
+                iso_id += niso
             self.db += databases
-            self.wn = np.concatenate((self.wn, wn))
-            self.gf = np.concatenate((self.gf, gf))
-            self.elow = np.concatenate((self.elow, elow))
+            cols['wn'].append(wn)
+            cols['gf'].append(gf)
+            cols['elow'].append(elow)
+            cols['isoid'].append(iso_id)
+        for key, parts in cols.items():
+            if len(parts) == 1:
+                setattr(self, key, parts[0])
+            elif parts:
+                setattr(self, key, np.concatenate(parts))
         self.isoid = np.asarray(self.isoid, int)
 
         self.tmin = np.amax([np.amin(db.temp) for db in self.db])

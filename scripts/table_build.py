@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--wl-high", type=float, default=30.0)
     ap.add_argument("--tmin", type=float, default=300.0)
     ap.add_argument("--tmax", type=float, default=3000.0)
+    ap.add_argument("--resolution", type=float, default=None,
+                    help="constant-R output grid (configs[2] variant) instead of --nwave points")
     ap.add_argument("--out", default=None, help="write the .npz table here (rank 0)")
     ap.add_argument("--gather", action="store_true", help="all-gather the table over NCCL")
     args = ap.parse_args()
@@ -58,7 +60,12 @@ def main():
     wnlow, wnhigh = 1.0 / (args.wl_high * pc.um), 1.0 / (args.wl_low * pc.um)
     wnstep = (wnhigh - wnlow) / (args.nwave - 1)
     wnosamp = int(_HCN[wnstep / _HCN <= 0.0004][0])
-    spec = Spectrum(wnlow=wnlow, wnhigh=wnhigh, wnstep=wnstep, wnosamp=wnosamp)
+    if args.resolution:
+        # reference defaults for constant-R grids: wnstep 1.0, wnosamp from the 4e-4 rule
+        spec = Spectrum(wnlow=wnlow, wnhigh=wnhigh, wnstep=1.0, resolution=args.resolution)
+        wnosamp = spec.wnosamp
+    else:
+        spec = Spectrum(wnlow=wnlow, wnhigh=wnhigh, wnstep=wnstep, wnosamp=wnosamp)
     press = pa.pressure(1e-6, 100.0, args.nlayers)
     vmr = np.tile(np.asarray(workloads.UNIFORM_VMR), (args.nlayers, 1))
     atm = pa.Atmosphere(press, np.full(args.nlayers, 1000.0), vmr, workloads.UNIFORM_SPECIES)
@@ -99,8 +106,8 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.time()
-    eng.extinction_batch(unit_t, dens, z[itemp], np.zeros(db.niso, int), 1, 1e-30, 0, 0,
-                         out_device_ptr=d_out.data_ptr())
+    eng.extinction_batch(unit_t, dens, z[itemp], np.zeros(db.niso, int), 1, 1e-30, 0,
+                         1 if args.resolution else 0, out_device_ptr=d_out.data_ptr())
     torch.cuda.synchronize()
     build_s = time.time() - t0
     tim = eng.last_timing()
