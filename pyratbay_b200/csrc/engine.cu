@@ -132,6 +132,8 @@ using namespace pb200;
 struct pb200_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // D2H of the first half of a batch while the second runs
+    cudaEvent_t ev_half = nullptr;
     cudaEvent_t ev[6] = {};
     int64_t launches = 0;
     double timing[5] = {0, 0, 0, 0, 0};
@@ -302,6 +304,8 @@ int pb200_engine_create(int device, pb200_engine **out) {
     e->device = device;
     cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && err == cudaSuccess; i++) err = cudaEventCreate(&e->ev[i]);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_half, cudaEventDisableTiming);
     if (err != cudaSuccess) {
         delete e;
         return cuda_fail(err, "engine create", __FILE__, __LINE__);
@@ -316,6 +320,8 @@ void pb200_engine_destroy(pb200_engine *e) {
     if (e->stream) {
         cudaStreamSynchronize(e->stream);
         cudaStreamDestroy(e->stream);
+        if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+        if (e->ev_half) cudaEventDestroy(e->ev_half);
     }
     for (int i = 0; i < 6; i++)
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -995,6 +1001,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         if (env && std::strcmp(env, "owner") == 0) chunked = 0;
     }
     float ms_strengths = 0.f, ms_accum = 0.f;
+    size_t copied_rows = 0, split_after = 0;  // rows already sent to the host by the copy stream
     // order units by strengths pass
     std::vector<int> order(n_units);
     for (int u = 0; u < n_units; u++) order[u] = u;
@@ -1039,6 +1046,20 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         for (size_t u0 = 0; u0 < cu.size();) {
             size_t u1 = u0;
             while (u1 < cu.size() && cmode[u1] == cmode[u0] && u1 - u0 < 65535) u1++;
+            // Host output: run the first half of the batch on its own, so that its rows travel
+            // to the host (copy stream) while the second half is computed.  Only when the
+            // first half is exactly the rows [0, half) of the caller's array.
+            if (out_host && !counters && u0 == 0 && tp0 == 0 && ntc == ntp && u1 == cu.size() &&
+                copied_rows == 0 && u1 >= 16) {
+                const size_t half = u1 / 2;
+                bool prefix = true;
+                for (size_t u = 0; u < u1 && prefix; u++)
+                    prefix = (u < half) == (cu[u].out_index < (int)half);
+                if (prefix) {
+                    u1 = half;
+                    split_after = half;
+                }
+            }
             const int nu = (int)(u1 - u0);
             rc = e->d_partial.alloc(ksplit > 1 ? (size_t)nu * nrows * ksplit * (size_t)nwave : 0);
             if (rc) return rc;
@@ -1054,6 +1075,14 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
                 if (rc) return rc;
                 if (V.ngroups > 0) e->launches++;
             }
+            if (split_after && u1 == split_after && copied_rows == 0) {
+                PB_CUDA(cudaEventRecord(e->ev_half, st));
+                PB_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_half, 0));
+                copied_rows = split_after;
+                PB_CUDA(cudaMemcpyAsync(out_host, d_out,
+                                        sizeof(double) * copied_rows * nrows * (size_t)nwave,
+                                        cudaMemcpyDeviceToHost, e->copy_stream));
+            }
             u0 = u1;
         }
         PB_CUDA(cudaEventRecord(e->ev[3], st));
@@ -1066,8 +1095,11 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         ms_accum += b;
     }
     PB_CUDA(cudaEventRecord(e->ev[3], st));
-    if (out_host)
-        PB_CUDA(cudaMemcpyAsync(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (out_host) {
+        const size_t done = sizeof(double) * copied_rows * nrows * (size_t)nwave;
+        PB_CUDA(cudaMemcpyAsync((char *)out_host + done, (const char *)d_out + done,
+                                out_bytes - done, cudaMemcpyDeviceToHost, st));
+    }
     std::vector<unsigned long long> cnt;
     if (counters) {
         cnt.resize((size_t)n_units * 4);
@@ -1079,6 +1111,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         PB_CUDA(cudaStreamWaitEvent(user_stream, e->ev[4], 0));
     }
     PB_CUDA(cudaStreamSynchronize(st));
+    if (copied_rows) PB_CUDA(cudaStreamSynchronize(e->copy_stream));
     if (counters) {
         // nadd is static per isotope: lines absorbed into a head line of a processed isotope
         int64_t nadd = 0;

@@ -62,6 +62,7 @@ class Line_By_Line:
         self.iso_ratio = np.zeros(niso)
         self.iso_atm_index = np.zeros(niso, int)
         self.iso_pf_interp = []
+        self._db_pf_interp = []
         mol_names = []
         total = 0
         for db in self.db:
@@ -78,6 +79,10 @@ class Line_By_Line:
             for j in range(db.niso):
                 self.iso_pf_interp.append(
                     sip.interp1d(db.temp, db.iso_pf[j], kind='slinear'))
+            # the same interpolant over all isotopes of the database at once (one SciPy call
+            # per database instead of one per isotope in `partition`; identical values)
+            self._db_pf_interp.append(
+                (sl, sip.interp1d(db.temp, db.iso_pf, kind='slinear', axis=-1)))
             total += db.niso
 
         # Single out an isotope if requested (line_by_line.py:161-175)
@@ -105,8 +110,8 @@ class Line_By_Line:
         """Z_i(T) [niso, len(T)] (line_by_line.py:219-222 and pyrat/extinction.py:90-92)."""
         temperature = np.atleast_1d(temperature)
         z = np.zeros((self.niso, len(temperature)), np.double)
-        for i in range(self.niso):
-            z[i] = self.iso_pf_interp[i](temperature)
+        for sl, interp in self._db_pf_interp:
+            z[sl] = interp(temperature)
         return z
 
     def calc_extinction_coefficient(self, temperature, density, layer=None, skip_mol=[]):
