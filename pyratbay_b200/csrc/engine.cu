@@ -189,12 +189,14 @@ struct pb200_engine {
     int nbins = 0, binw = 1;
 
     // per-batch scratch (grown on demand)
-    DevBuf<double> d_ksum, d_tp_temp, d_tp_isoz, d_out, d_partial;
+    DevBuf<double> d_ksum, d_out, d_partial;
     int sm_count = 0;
     DevBuf<unsigned long long> d_kmax, d_counters;
-    DevBuf<UnitParams> d_units;
-    DevBuf<IsoUnit> d_iso_units;
-    DevBuf<int> d_iso_row;
+    // per-batch scalars (iso_row, 1/T, 1/Z, UnitParams, IsoUnit) travel in ONE copy from a
+    // pinned staging block
+    DevBuf<char> d_stage;
+    char *h_stage = nullptr;
+    size_t h_stage_bytes = 0;
 
     StaticView view() const {
         StaticView V;
@@ -321,6 +323,7 @@ void pb200_engine_destroy(pb200_engine *e) {
         cudaStreamSynchronize(e->stream);
         cudaStreamDestroy(e->stream);
         if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+        if (e->h_stage) cudaFreeHost(e->h_stage);
         if (e->ev_half) cudaEventDestroy(e->ev_half);
     }
     for (int i = 0; i < 6; i++)
@@ -956,11 +959,22 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
 
     rc = e->d_ksum.alloc((size_t)tp_chunk * (size_t)std::max<int64_t>(e->ngroups, 1));
     if (!rc) rc = e->d_kmax.alloc((size_t)tp_chunk * nrows);
-    if (!rc) rc = e->d_tp_temp.alloc(tp_chunk);
-    if (!rc) rc = e->d_tp_isoz.alloc((size_t)tp_chunk * niso);
-    if (!rc) rc = e->d_units.alloc(n_units);
-    if (!rc) rc = e->d_iso_units.alloc((size_t)n_units * niso);
-    if (!rc) rc = e->d_iso_row.alloc(niso);
+    // staging block layout (every section 16-byte aligned)
+    auto align16 = [](size_t n) { return (n + 15) & ~(size_t)15; };
+    const size_t off_row = 0;
+    const size_t off_invt = off_row + align16(sizeof(int) * niso);
+    const size_t off_invz = off_invt + align16(sizeof(double) * tp_chunk);
+    const size_t off_units = off_invz + align16(sizeof(double) * (size_t)tp_chunk * niso);
+    const size_t off_iso = off_units + align16(sizeof(UnitParams) * (size_t)n_units);
+    const size_t stage_bytes = off_iso + align16(sizeof(IsoUnit) * (size_t)n_units * niso);
+    if (!rc) rc = e->d_stage.alloc(stage_bytes);
+    if (!rc && e->h_stage_bytes < stage_bytes) {
+        if (e->h_stage) cudaFreeHost(e->h_stage);
+        e->h_stage = nullptr;
+        e->h_stage_bytes = 0;
+        PB_CUDA(cudaHostAlloc((void **)&e->h_stage, stage_bytes, cudaHostAllocDefault));
+        e->h_stage_bytes = stage_bytes;
+    }
     if (!rc && counters) rc = e->d_counters.alloc((size_t)n_units * 4);
     if (rc) return rc;
 
@@ -970,8 +984,6 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         PB_CUDA(cudaStreamWaitEvent(st, e->ev[5], 0));
     }
     PB_CUDA(cudaEventRecord(e->ev[0], st));
-    PB_CUDA(cudaMemcpyAsync(e->d_iso_row.p, iso_row.data(), sizeof(int) * niso,
-                            cudaMemcpyHostToDevice, st));
     if (counters) PB_CUDA(cudaMemsetAsync(e->d_counters.p, 0, sizeof(unsigned long long) * n_units * 4, st));
 
     const StaticView V = e->view();
@@ -1027,17 +1039,21 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
                           iso_units.begin() + (size_t)(u + 1) * niso);
             }
         }
-        PB_CUDA(cudaMemcpyAsync(e->d_tp_temp.p, tp_inv_t.data() + tp0, sizeof(double) * ntc,
-                                cudaMemcpyHostToDevice, st));
-        PB_CUDA(cudaMemcpyAsync(e->d_tp_isoz.p, tp_inv_z.data() + (size_t)tp0 * niso,
-                                sizeof(double) * ntc * niso, cudaMemcpyHostToDevice, st));
-        PB_CUDA(cudaMemcpyAsync(e->d_units.p, cu.data(), sizeof(UnitParams) * cu.size(),
-                                cudaMemcpyHostToDevice, st));
-        PB_CUDA(cudaMemcpyAsync(e->d_iso_units.p, ci.data(), sizeof(IsoUnit) * ci.size(),
-                                cudaMemcpyHostToDevice, st));
+        std::memcpy(e->h_stage + off_row, iso_row.data(), sizeof(int) * niso);
+        std::memcpy(e->h_stage + off_invt, tp_inv_t.data() + tp0, sizeof(double) * ntc);
+        std::memcpy(e->h_stage + off_invz, tp_inv_z.data() + (size_t)tp0 * niso,
+                    sizeof(double) * ntc * niso);
+        std::memcpy(e->h_stage + off_units, cu.data(), sizeof(UnitParams) * cu.size());
+        std::memcpy(e->h_stage + off_iso, ci.data(), sizeof(IsoUnit) * ci.size());
+        PB_CUDA(cudaMemcpyAsync(e->d_stage.p, e->h_stage, stage_bytes, cudaMemcpyHostToDevice, st));
+        const int *p_iso_row = reinterpret_cast<const int *>(e->d_stage.p + off_row);
+        const double *p_inv_t = reinterpret_cast<const double *>(e->d_stage.p + off_invt);
+        const double *p_inv_z = reinterpret_cast<const double *>(e->d_stage.p + off_invz);
+        const UnitParams *p_units = reinterpret_cast<const UnitParams *>(e->d_stage.p + off_units);
+        const IsoUnit *p_iso_units = reinterpret_cast<const IsoUnit *>(e->d_stage.p + off_iso);
         PB_CUDA(cudaMemsetAsync(e->d_kmax.p, 0, sizeof(unsigned long long) * ntc * nrows, st));
         PB_CUDA(cudaEventRecord(e->ev[1], st));
-        rc = launch_strengths(st, V, ntc, e->d_tp_temp.p, e->d_tp_isoz.p, e->d_iso_row.p, nrows,
+        rc = launch_strengths(st, V, ntc, p_inv_t, p_inv_z, p_iso_row, nrows,
                               e->d_ksum.p, e->d_kmax.p, e->d_lgroup.p, e->d_liso.p, e->n_inwin);
         if (rc) return rc;
         if (V.ngroups > 0) e->launches++;
@@ -1063,14 +1079,14 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
             const int nu = (int)(u1 - u0);
             rc = e->d_partial.alloc(ksplit > 1 ? (size_t)nu * nrows * ksplit * (size_t)nwave : 0);
             if (rc) return rc;
-            rc = launch_accumulate(st, V, nu, e->d_units.p + u0, e->d_iso_units.p + u0 * niso,
-                                   e->d_iso_row.p, e->d_ksum.p, e->d_kmax.p, nrows, ethresh,
+            rc = launch_accumulate(st, V, nu, p_units + u0, p_iso_units + u0 * niso,
+                                   p_iso_row, e->d_ksum.p, e->d_kmax.p, nrows, ethresh,
                                    cutoff, cmode[u0], d_out, ksplit, e->d_partial.p, chunked);
             if (rc) return rc;
             e->launches += ksplit > 1 ? 2 : 1;
             if (counters) {
-                rc = launch_counters(st, V, nu, e->d_units.p + u0, e->d_iso_units.p + u0 * niso,
-                                     e->d_iso_row.p, e->d_ksum.p, e->d_kmax.p, nrows, ethresh,
+                rc = launch_counters(st, V, nu, p_units + u0, p_iso_units + u0 * niso,
+                                     p_iso_row, e->d_ksum.p, e->d_kmax.p, nrows, ethresh,
                                      cutoff, resolution ? 1 : 0, e->d_counters.p);
                 if (rc) return rc;
                 if (V.ngroups > 0) e->launches++;
