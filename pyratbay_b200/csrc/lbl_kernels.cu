@@ -99,12 +99,8 @@ __device__ __forceinline__ bool prepare_group(const StaticView &V, const UnitPar
 
 // ---------------------------------------------------------------------------------------
 // Kernel 1: line strengths per (T, Z) pass, summed per co-add group, and the per-row maximum.
-// Divisions by T and Z as multiplications by reciprocals taken once per thread: what the
+// Divisions by T and Z are multiplications by reciprocals rounded once on the host: what the
 // reference's own -O3 -ffast-math build does; <= 1 ulp per factor (1e-15 on the strength).
-// Measured 1.11 -> 1.00 ms at configs[1].  0 keeps the three IEEE divisions per line.
-#ifndef PB200_STR_RECIP
-#define PB200_STR_RECIP 1
-#endif
 #ifndef PB200_STR_MINBLOCKS
 #define PB200_STR_MINBLOCKS 4
 #endif
