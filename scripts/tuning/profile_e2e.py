@@ -1,7 +1,7 @@
 """cProfile of the host side of the e2e step (Pyrat.calc_lbl_extinction) on configs[1]."""
 import cProfile, pstats, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from pyratbay_b200 import workloads, tli as ptli
 from pyratbay_b200.pyrat import Pyrat
