@@ -429,6 +429,22 @@ PB200_PRAGMA_UNROLL
 #endif
 #define PB200_CHUNK_BOUNDS __launch_bounds__(256, PB200_CHUNK_MINBLOCKS)
 
+// 8-byte gather of a table sample.  PB200_GATHER_NOALLOC=1 (ld.global.nc.L1::no_allocate) was
+// measured and rejected: 2.35 -> 3.48 ms at configs[1], 0.59 -> 1.04 s for the 1e7-line table
+// (the L1 hit rate is only 8 %, but the allocating path merges the sectors of a request).
+#ifndef PB200_GATHER_NOALLOC
+#define PB200_GATHER_NOALLOC 0
+#endif
+__device__ __forceinline__ double gather_sample(const double *p) {
+#if PB200_GATHER_NOALLOC
+    double v;
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 // One empty asm that "modifies" all N values: everything that produces them (the gathers) is
 // scheduled before it, everything that consumes them after it.
 template <int N>
@@ -485,7 +501,7 @@ __device__ __forceinline__ double run_slots(const double2 *__restrict__ slots, i
             const double2 s = mine[(i + j) * R];
             kk[j] = s.x;
             vv[j] = 0.0;
-            if ((unsigned)__double2hiint(s.y) & bit) vv[j] = __ldg(lane_ptr + __double2loint(s.y));
+            if ((unsigned)__double2hiint(s.y) & bit) vv[j] = gather_sample(lane_ptr + __double2loint(s.y));
         }
         // ...before the first sample is consumed (U loads in flight per warp; without this
         // fence ptxas interleaves each FMA right behind its load)
@@ -536,9 +552,9 @@ __device__ __forceinline__ void run_multi(const double2 *__restrict__ slots, int
                 if (q == P - 1) on = on && lane < bl;
                 if (q == 0 || q == P - 1) {
                     vv[j * P + q] = 0.0;
-                    if (on) vv[j * P + q] = __ldg(src + 32 * q);
+                    if (on) vv[j * P + q] = gather_sample(src + 32 * q);
                 } else {
-                    vv[j * P + q] = __ldg(src + 32 * q);
+                    vv[j * P + q] = gather_sample(src + 32 * q);
                 }
             }
         }
