@@ -436,9 +436,17 @@ PB200_PRAGMA_UNROLL
 #define PB200_GATHER_NOALLOC 0
 #endif
 __device__ __forceinline__ double gather_sample(const double *p) {
-#if PB200_GATHER_NOALLOC
+#if PB200_GATHER_NOALLOC == 1
     double v;
     asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#elif PB200_GATHER_NOALLOC == 2
+    double v;
+    asm("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#elif PB200_GATHER_NOALLOC == 3
+    double v;
+    asm("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 #else
     return __ldg(p);
