@@ -177,6 +177,7 @@ def test_forward_model_matches_reference():
     dict(cutoff=0.0, extent=20.0),                     # no fixed cutoff
     dict(resolution=8000.0),                           # constant-R (2-point interpolation)
     dict(nlines=200000, wnosamp=120),                  # dense: heavy co-adding
+    dict(nlines=400000, wnosamp=60),                   # co-add groups longer than a warp
     dict(wnstep=0.25, wnosamp=360, wnlow=9000.0, wnhigh=9060.0),
     dict(nlines=300, wnlow=9000.0, wnhigh=9600.0),     # sparse: chunks span many outputs
     dict(nlines=4000, wnstep=0.1, wnosamp=240, wnlow=9000.0, wnhigh=9030.0),  # > 8 passes/line
