@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -990,17 +991,18 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
     // Tile split: when a unit has far fewer tiles than there are resident CTAs (4 per SM),
     // several CTAs share a tile (each takes every ksplit-th chunk of the candidate lists) so
     // that fewer units are in flight at once and their Voigt profiles stay longer in L2.
-    // Measured at configs[1] (71 tiles): ksplit 1/2/4/8/16 -> 4.25/3.84/3.85/4.09/4.58 ms.
+    // Measured at configs[1] with the chunk kernel and 512-wide tiles (36 tiles): ksplit
+    // 2/4/8/16 -> 2.68/2.31/2.26/2.45 ms.
     if (e->sm_count == 0) cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device);
     int ksplit = 1;
     {
-        const long long ntiles = (nwave + kTileOutputs - 1) / kTileOutputs;
+        const long long ntiles = (nwave + kChunkTile - 1) / kChunkTile;
         const long long resident = 4LL * std::max(e->sm_count, 1);
-        ksplit = (int)std::max<long long>(1, std::min<long long>(4, resident / std::max<long long>(2 * ntiles * nrows, 1)));
-        // ...but only while every warp keeps >= 8 chunks of 32 groups (sparse lists: the fixed
-        // cost per CTA dominates; 1e5 lines: ksplit 4/2/1 -> 0.60/0.52/0.49 ms)
+        ksplit = (int)std::max<long long>(1, std::min<long long>(8, resident / std::max<long long>(2 * ntiles * nrows, 1)));
+        // ...but only while every warp keeps >= 4 chunks of 32 groups (sparse lists: the fixed
+        // cost per CTA dominates; 1e5 lines, 512-wide tiles: ksplit 1/2/4 -> 0.55/0.50/0.51 ms)
         const long long chunks_per_tile = e->ngroups / std::max<long long>(ntiles, 1) / 32;
-        ksplit = (int)std::max<long long>(1, std::min<long long>(ksplit, chunks_per_tile / 64));
+        ksplit = (int)std::max<long long>(1, std::min<long long>(ksplit, chunks_per_tile / 32));
         const char *env = std::getenv("PB200_KSPLIT");
         if (env && std::atoi(env) >= 1) ksplit = std::min(64, std::atoi(env));
     }
@@ -1226,9 +1228,22 @@ static int interp_impl(int device, double *ext, const double *etable, bool on_de
     std::copy(w_hi.begin(), w_hi.end(), packed.begin() + nlayers);
     std::copy(density, density + (size_t)nlayers * nspec, packed.begin() + 2 * (size_t)nlayers);
     std::memcpy(packed.data() + ndbl, tlo.data(), sizeof(int) * nlayers);
+    // (a persistent per-device scratch block: a stream-ordered allocation freed before the
+    // synchronize returned its memory to the OS on every call, 0.5 ms for a 69 us kernel)
     double *d_small = nullptr;
+    static std::mutex mu;  // held until the call has synchronised: the block is shared
+    std::lock_guard<std::mutex> lock(mu);
     {
-        cudaError_t ea = cudaMallocAsync((void **)&d_small, sizeof(double) * packed.size(), st);
+        static std::map<int, std::pair<double *, size_t>> scratch;  // device -> (block, doubles)
+        auto &slot = scratch[device];
+        cudaError_t ea = cudaSuccess;
+        if (slot.second < packed.size()) {
+            if (slot.first) cudaFree(slot.first);
+            slot = {nullptr, 0};
+            ea = cudaMalloc((void **)&slot.first, sizeof(double) * packed.size());
+            if (ea == cudaSuccess) slot.second = packed.size();
+        }
+        d_small = slot.first;
         if (ea == cudaSuccess)
             ea = cudaMemcpyAsync(d_small, packed.data(), sizeof(double) * packed.size(),
                                  cudaMemcpyHostToDevice, st);
@@ -1246,7 +1261,6 @@ static int interp_impl(int device, double *ext, const double *etable, bool on_de
         rc = launch_interp_ec(st, dext, tab, (const int *)(d_small + ndbl), d_small,
                               d_small + nlayers, d_small + 2 * (size_t)nlayers, nspec, ntemp,
                               nlayers, nwave, lay1, lay2, per_mol);
-    if (d_small) cudaFreeAsync(d_small, st);
     if (!rc && !on_device) {
         cudaError_t e2 = cudaMemcpyAsync(ext, dext, sizeof(double) * ext_n,
                                          cudaMemcpyDeviceToHost, st);

@@ -6,7 +6,11 @@
 
 namespace pb200 {
 
-constexpr int kTileOutputs = 256;  // output samples owned by one CTA of the accumulate kernel
+constexpr int kTileOutputs = 256;  // output samples owned by one CTA of the output-owned kernel
+#ifndef PB200_CHUNK_TILE
+#define PB200_CHUNK_TILE 512
+#endif
+constexpr int kChunkTile = PB200_CHUNK_TILE;  // ... of the chunk-owned kernel (multiple of 256)
 constexpr int kMaxIso = 256;
 
 // Exact division of a non-negative 31-bit integer by a launch-invariant divisor with one

@@ -429,6 +429,14 @@ PB200_PRAGMA_UNROLL
 #endif
 #define PB200_CHUNK_BOUNDS __launch_bounds__(256, PB200_CHUNK_MINBLOCKS)
 
+// 16-byte load of a staged slot through a 32-bit shared-memory address (a generic pointer makes
+// the compiler rebuild the shared window base inside the slot loops).
+__device__ __forceinline__ double2 load_slot16(unsigned saddr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(saddr));
+    return v;
+}
+
 // 8-byte gather of a table sample.  PB200_GATHER_NOALLOC=1 (ld.global.nc.L1::no_allocate) was
 // measured and rejected: 2.35 -> 3.48 ms at configs[1], 0.59 -> 1.04 s for the 1e7-line table
 // (the L1 hit rate is only 8 %, but the allocating path merges the sectors of a request).
@@ -495,7 +503,8 @@ __device__ __forceinline__ double run_slots(const double2 *__restrict__ slots, i
     constexpr int U = PB200_CHUNK_UNROLL < 32 / R ? PB200_CHUNK_UNROLL : 32 / R;
     unsigned bit = 1u << (lane & (W - 1));
     asm volatile("" : "+r"(bit));  // keep the mask test one LOP3 (not shift + and + compare)
-    const double2 *__restrict__ mine = slots + (R > 1 ? lane / W : 0);
+    unsigned mine = (unsigned)__cvta_generic_to_shared(slots + (R > 1 ? lane / W : 0));
+    asm volatile("" : "+r"(mine));
     // keep the lane's table pointer in a register pair: one IMAD.WIDE per slot address
     asm volatile("" : "+l"(lane_ptr));
     // slots beyond nslots carry an empty mask, so the trip count is rounded up to the unroll
@@ -506,7 +515,7 @@ __device__ __forceinline__ double run_slots(const double2 *__restrict__ slots, i
         double kk[U], vv[U];
 #pragma unroll
         for (int j = 0; j < U; j++) {
-            const double2 s = mine[(i + j) * R];
+            const double2 s = load_slot16(mine + 16u * (unsigned)((i + j) * R));
             kk[j] = s.x;
             vv[j] = 0.0;
             if ((unsigned)__double2hiint(s.y) & bit) vv[j] = gather_sample(lane_ptr + __double2loint(s.y));
@@ -540,6 +549,8 @@ __device__ __forceinline__ void run_multi(const double2 *__restrict__ slots, int
                                           const double *lane_ptr, int lane, double (&acc)[P]) {
     constexpr int U = P == 1 ? PB200_CHUNK_UNROLL : (P == 2 ? 8 : (P <= 4 ? 4 : 2));
     asm volatile("" : "+l"(lane_ptr));
+    unsigned sbase = (unsigned)__cvta_generic_to_shared(slots);
+    asm volatile("" : "+r"(sbase));  // keep it in a register (else rebuilt in every iteration)
     const int niter = (nslots + U - 1) / U * U;  // tail slots: k = 0, offset 0 (valid address)
 #pragma unroll
     for (int q = 0; q < P; q++) acc[q] = 0.0;
@@ -548,7 +559,7 @@ __device__ __forceinline__ void run_multi(const double2 *__restrict__ slots, int
         double kk[U], vv[U * P];
 #pragma unroll
         for (int j = 0; j < U; j++) {
-            const double2 s = slots[i + j];
+            const double2 s = load_slot16(sbase + 16u * (unsigned)(i + j));
             kk[j] = s.x;
             const double *src = lane_ptr + __double2loint(s.y);
             const int w = __double2hiint(s.y);
@@ -620,7 +631,7 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                          double cutoff, double *__restrict__ out, int ksplit,
                          double *__restrict__ partial) {
     extern __shared__ double s_doppler[];           // [ndop]
-    __shared__ double s_acc[8][kTileOutputs];       // per-warp private copy of the tile
+    __shared__ double s_acc[8][kChunkTile];         // per-warp private copy of the tile
     __shared__ double2 s_slot[8][32];
     __shared__ int2 s_range[kMaxIso];               // candidate groups [glo, ghi) per isotope
 
@@ -628,14 +639,14 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
     for (int i = threadIdx.x; i < V.ndop; i += blockDim.x)
         s_doppler[i] = V.dop_thr ? V.dop_thr[i] : V.doppler[i];
 #pragma unroll
-    for (int i = 0; i < kTileOutputs / 32; i++) s_acc[warp][i * 32 + lane] = 0.0;
+    for (int i = 0; i < kChunkTile / 32; i++) s_acc[warp][i * 32 + lane] = 0.0;
     __syncthreads();
 
     const UnitParams U = units[blockIdx.y];
     const int row = blockIdx.z;
     const int tile = blockIdx.x / ksplit, split = blockIdx.x - tile * ksplit;
-    const int m0 = tile * kTileOutputs;
-    const int tile_hi = min(m0 + kTileOutputs, min(V.nwave, U.mcount));  // exclusive
+    const int m0 = tile * kChunkTile;
+    const int tile_hi = min(m0 + kChunkTile, min(V.nwave, U.mcount));  // exclusive
     const double *__restrict__ ks = ksum + (size_t)U.tpass * V.ngroups;
     double *acc_tile = s_acc[warp];
     double2 *slots = s_slot[warp];
@@ -775,15 +786,18 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
         }
     }
     __syncthreads();
-    const int m = m0 + threadIdx.x;
-    if (m < V.nwave) {
-        double sum = s_acc[0][threadIdx.x];
+    double *dst = ksplit > 1
+        ? partial + (((size_t)blockIdx.y * nrows + row) * ksplit + split) * (size_t)V.nwave
+        : out + ((size_t)U.out_index * nrows + row) * (size_t)V.nwave;
 #pragma unroll
-        for (int w = 1; w < 8; w++) sum += s_acc[w][threadIdx.x];
-        double *dst = ksplit > 1
-            ? partial + (((size_t)blockIdx.y * nrows + row) * ksplit + split) * (size_t)V.nwave
-            : out + ((size_t)U.out_index * nrows + row) * (size_t)V.nwave;
-        dst[m] = sum;  // 0 beyond mcount
+    for (int t = threadIdx.x; t < kChunkTile; t += 256) {
+        const int m = m0 + t;
+        if (m < V.nwave) {
+            double sum = s_acc[0][t];
+#pragma unroll
+            for (int w = 1; w < 8; w++) sum += s_acc[w][t];
+            dst[m] = sum;  // 0 beyond mcount
+        }
     }
 }
 
@@ -988,7 +1002,8 @@ int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
                       double *partial, int chunked) {
     if (nunits == 0 || V.nwave == 0) return 0;
     if (ksplit < 1 || !partial) ksplit = 1;
-    const int ntiles = (V.nwave + kTileOutputs - 1) / kTileOutputs;
+    const int tile_w = (mode == kTransposed && chunked) ? kChunkTile : kTileOutputs;
+    const int ntiles = (V.nwave + tile_w - 1) / tile_w;
     dim3 grid((unsigned)(ntiles * ksplit), (unsigned)nunits, (unsigned)nrows);
     const size_t smem = sizeof(double) * V.ndop;
     if (mode == kTransposed && chunked)
