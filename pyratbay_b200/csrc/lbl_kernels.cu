@@ -630,8 +630,11 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                          const unsigned long long *__restrict__ kmax, int nrows, double ethresh,
                          double cutoff, double *__restrict__ out, int ksplit,
                          double *__restrict__ partial) {
-    extern __shared__ double s_doppler[];           // [ndop]
-    __shared__ double s_acc[8][kChunkTile];         // per-warp private copy of the tile
+    // dynamic shared memory: [8][kChunkTile] per-warp private copies of the tile, then the
+    // Doppler thresholds [ndop]
+    extern __shared__ double s_dyn[];
+    double (*s_acc)[kChunkTile] = reinterpret_cast<double (*)[kChunkTile]>(s_dyn);
+    double *s_doppler = s_dyn + 8 * kChunkTile;
     __shared__ double2 s_slot[8][32];
     __shared__ int2 s_range[kMaxIso];               // candidate groups [glo, ghi) per isotope
 
@@ -1006,7 +1009,19 @@ int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
     const int ntiles = (V.nwave + tile_w - 1) / tile_w;
     dim3 grid((unsigned)(ntiles * ksplit), (unsigned)nunits, (unsigned)nrows);
     const size_t smem = sizeof(double) * V.ndop;
-    if (mode == kTransposed && chunked)
+    if (mode == kTransposed && chunked) {
+        const size_t csmem = smem + sizeof(double) * 8 * kChunkTile;
+        static bool opted_in = false;  // > 48 KB of dynamic shared memory needs the opt-in
+        if (!opted_in) {
+            PB_CUDA(cudaFuncSetAttribute(accumulate_chunks_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(double) * 8 * kChunkTile + 8 * 4096)));
+            opted_in = true;
+        }
+        if (V.ndop > 4096) return cuda_fail(cudaErrorInvalidValue, "ndop > 4096", __FILE__, __LINE__);
+        accumulate_chunks_kernel<<<grid, 256, csmem, st>>>(
+            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
+    } else if (mode == kTransposed && chunked)
         accumulate_chunks_kernel<<<grid, 256, smem, st>>>(
             V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
     else if (mode == kLinterp)
