@@ -1011,20 +1011,14 @@ int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
     const size_t smem = sizeof(double) * V.ndop;
     if (mode == kTransposed && chunked) {
         const size_t csmem = smem + sizeof(double) * 8 * kChunkTile;
-        static bool opted_in = false;  // > 48 KB of dynamic shared memory needs the opt-in
-        if (!opted_in) {
+        // more than 48 KB of dynamic shared memory needs the per-device opt-in (not the case
+        // for 512-output tiles unless the Doppler grid is huge)
+        if (csmem > 48 * 1024)
             PB_CUDA(cudaFuncSetAttribute(accumulate_chunks_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(sizeof(double) * 8 * kChunkTile + 8 * 4096)));
-            opted_in = true;
-        }
-        if (V.ndop > 4096) return cuda_fail(cudaErrorInvalidValue, "ndop > 4096", __FILE__, __LINE__);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
         accumulate_chunks_kernel<<<grid, 256, csmem, st>>>(
             V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
-    } else if (mode == kTransposed && chunked)
-        accumulate_chunks_kernel<<<grid, 256, smem, st>>>(
-            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
-    else if (mode == kLinterp)
+    } else if (mode == kLinterp)
         accumulate_kernel<kLinterp><<<grid, 256, smem, st>>>(
             V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
     else if (mode == kTransposed)
