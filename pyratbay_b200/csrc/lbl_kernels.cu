@@ -126,7 +126,10 @@ __device__ __forceinline__ double line_strength(double w, double elow, double gf
 // The maximum is taken over every single line (:225): warp REDUX of the IEEE bit pattern
 // (kprop >= 0 orders like its bits), one atomic per warp and pass, skipped when the running
 // maximum is already larger.
-constexpr int kStrTemps = 8;
+#ifndef PB200_STR_TEMPS
+#define PB200_STR_TEMPS 32   // <= 32: lane j keeps the maximum of pass j
+#endif
+constexpr int kStrTemps = PB200_STR_TEMPS;
 
 __global__ void __launch_bounds__(256, PB200_STR_MINBLOCKS)
 strengths_kernel(StaticView V, const int *__restrict__ l_group,
@@ -422,7 +425,7 @@ PB200_PRAGMA_UNROLL
 // Staged slot (16 bytes, one broadcast LDS.128): {k, table offset of the sample of output
 // lo_min (int32), lane mask of the current pass}.  Needs tlen + nwave < 2^31.
 #ifndef PB200_CHUNK_UNROLL
-#define PB200_CHUNK_UNROLL 16
+#define PB200_CHUNK_UNROLL 8
 #endif
 #ifndef PB200_CHUNK_MINBLOCKS
 #define PB200_CHUNK_MINBLOCKS 4
