@@ -157,7 +157,7 @@ def ncu_traffic(args):
     the default workload it was taken on."""
     default = (args.nlines == 1_000_000 and args.nlayers == 81 and args.wl_low == 0.5
                and args.wl_high == 5.0 and args.ptop == 1e-6 and args.pbottom == 100.0)
-    return 1.506374e9 + 105.745920e6 if default else None
+    return 1.491280e9 + 90.537728e6 if default else None
 
 
 def run_b200(args):
