@@ -116,28 +116,27 @@ class Linelist:
 
     @staticmethod
     def binsearch_array(wave_of, target, ilo, ihi, searchup=True):
-        """driver.py:80-137 with `wave_of(irec)` instead of a file seek."""
-        imin, imax = ilo, ihi
-        while ihi - ilo > 1:
-            irec = (ihi + ilo) // 2
-            if wave_of(irec) > target:
-                ihi = irec
+        """Record index for `target` with the semantics of the reference's file search
+        (driver.py:80-137), `wave_of(irec)` replacing its seek + read: a bisection that keeps
+        wave(lo) <= target < wave(hi), then a walk over neighbouring records (up from `lo`
+        while the next record is still below the target, or down from `hi` while the previous
+        one is still above it) that stops at either end of the search range."""
+        first, last = ilo, ihi
+        lo, hi = ilo, ihi
+        while hi - lo > 1:
+            mid = (hi + lo) // 2
+            if wave_of(mid) > target:
+                hi = mid
             else:
-                ilo = irec
-        irec = ilo if searchup else ihi
-        icheck = irec
-        bounded = True
-        while bounded:
-            irec = icheck
-            if irec == imin or irec == imax:
+                lo = mid
+        step = 1 if searchup else -1
+        pos = lo if searchup else hi
+        while pos != first and pos != last:
+            neighbour = wave_of(pos + step)
+            if not (neighbour < target if searchup else neighbour > target):
                 break
-            if searchup:
-                icheck += 1
-                bounded = wave_of(icheck) < target
-            else:
-                icheck -= 1
-                bounded = wave_of(icheck) > target
-        return irec
+            pos += step
+        return pos
 
     def _window(self, wn_all, iwn, fwn):
         """Record range [istart, istop] of the reference's dbread, or None (no overlap)."""
