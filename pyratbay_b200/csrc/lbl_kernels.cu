@@ -418,8 +418,8 @@ PB200_PRAGMA_UNROLL
 // [lo_min, hi_max): ceil(F/32) passes per chunk, every pass with (nearly) all lanes inside.
 // Chunks whose footprint is <= 16 (<= 8) outputs wide run two (four) groups per instruction
 // on half (quarter) warps.  A pass accumulates its 32 slots in a register and adds the sum
-// once to the warp's PRIVATE copy of the CTA's 256-output tile in shared memory; the eight
-// copies are summed in a fixed order at the end (no atomics, deterministic).
+// once to the warp's PRIVATE copy of the CTA's tile (kChunkTile = 512 outputs) in shared
+// memory; the eight copies are summed in a fixed order at the end (no atomics, deterministic).
 // The chunk list of a tile (all isotopes) is split evenly over the 8*ksplit warps working
 // on the tile, so the work of a CTA is balanced whatever the line density.
 // Staged slot (16 bytes, one broadcast LDS.128): {k, table offset of the sample of output
