@@ -430,7 +430,6 @@ PB200_PRAGMA_UNROLL
 #ifndef PB200_CHUNK_MINBLOCKS
 #define PB200_CHUNK_MINBLOCKS 4
 #endif
-#define PB200_CHUNK_BOUNDS __launch_bounds__(256, PB200_CHUNK_MINBLOCKS)
 
 // 16-byte load of a staged slot through a 32-bit shared-memory address (a generic pointer makes
 // the compiler rebuild the shared window base inside the slot loops).
@@ -499,11 +498,11 @@ __device__ __forceinline__ void issue_fence(double (&v)[N]) {
 }
 
 // Run the staged slots of one pass: W lanes per slot, 32/W slots per instruction.
-template <int W>
+template <int W, int UNR>
 __device__ __forceinline__ double run_slots(const double2 *__restrict__ slots, int nslots,
                                             const double *lane_ptr, int lane) {
     constexpr int R = 32 / W;                      // slots per instruction
-    constexpr int U = PB200_CHUNK_UNROLL < 32 / R ? PB200_CHUNK_UNROLL : 32 / R;
+    constexpr int U = UNR < 32 / R ? UNR : 32 / R;
     unsigned bit = 1u << (lane & (W - 1));
     asm volatile("" : "+r"(bit));  // keep the mask test one LOP3 (not shift + and + compare)
     unsigned mine = (unsigned)__cvta_generic_to_shared(slots + (R > 1 ? lane / W : 0));
@@ -547,10 +546,10 @@ __device__ __forceinline__ double run_slots(const double2 *__restrict__ slots, i
 // Staged word 3 = a | bL << 8: first lane of pass 0, one-past-last lane of pass P-1.
 // The shared-memory/L1 data pipe is what bounds this kernel (2 cycles per broadcast, 2 per
 // 256-byte gather): P passes cost 2 + 2P instead of 4P cycles.
-template <int P>
+template <int P, int UNR>
 __device__ __forceinline__ void run_multi(const double2 *__restrict__ slots, int nslots,
                                           const double *lane_ptr, int lane, double (&acc)[P]) {
-    constexpr int U = P == 1 ? PB200_CHUNK_UNROLL : (P == 2 ? 8 : (P <= 4 ? 4 : 2));
+    constexpr int U = P == 1 ? UNR : (P == 2 ? 8 : (P <= 4 ? 4 : 2));
     asm volatile("" : "+l"(lane_ptr));
     unsigned sbase = (unsigned)__cvta_generic_to_shared(slots);
     asm volatile("" : "+r"(sbase));  // keep it in a register (else rebuilt in every iteration)
@@ -592,12 +591,12 @@ __device__ __forceinline__ void run_multi(const double2 *__restrict__ slots, int
     if (P == 1) acc[0] += odd;
 }
 
-template <int P>
+template <int P, int UNR>
 __device__ __forceinline__ void run_multi_store(const double2 *slots, int nslots,
                                                 const double *lane_ptr, int lane,
                                                 double *acc_rel, int span) {
     double acc[P];
-    run_multi<P>(slots, nslots, lane_ptr, lane, acc);
+    run_multi<P, UNR>(slots, nslots, lane_ptr, lane, acc);
 #pragma unroll
     for (int q = 0; q < P; q++)
         if (32 * q + lane < span) acc_rel[32 * q + lane] += acc[q];
@@ -626,7 +625,11 @@ __device__ __forceinline__ bool candidate_range(const StaticView &V, const UnitP
     return *ghi > *glo;
 }
 
-__global__ void PB200_CHUNK_BOUNDS
+// Two instantiations: <4 CTAs/SM, gather batch 8> for footprints of one or two passes
+// (forward models, 1 cm-1 steps) and <3 CTAs/SM, batch 16> for wide footprints (table grids with
+// >= 3 passes per line: 517 vs 539 ms at 1e7 lines, but 7 % slower at configs[1]).
+template <int MINB, int UNR>
+__global__ void __launch_bounds__(256, MINB)
 accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                          const IsoUnit *__restrict__ iso_units, const int *__restrict__ iso_row,
                          const double *__restrict__ ksum,
@@ -744,14 +747,14 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                     __syncwarp();
                     const double *lp = V.tprofile + lane;
                     switch (npass) {
-                    case 1: run_multi_store<1>(slots, nval, lp, lane, acc_rel, span); break;
-                    case 2: run_multi_store<2>(slots, nval, lp, lane, acc_rel, span); break;
-                    case 3: run_multi_store<3>(slots, nval, lp, lane, acc_rel, span); break;
-                    case 4: run_multi_store<4>(slots, nval, lp, lane, acc_rel, span); break;
-                    case 5: run_multi_store<5>(slots, nval, lp, lane, acc_rel, span); break;
-                    case 6: run_multi_store<6>(slots, nval, lp, lane, acc_rel, span); break;
-                    case 7: run_multi_store<7>(slots, nval, lp, lane, acc_rel, span); break;
-                    default: run_multi_store<8>(slots, nval, lp, lane, acc_rel, span); break;
+                    case 1: run_multi_store<1, UNR>(slots, nval, lp, lane, acc_rel, span); break;
+                    case 2: run_multi_store<2, UNR>(slots, nval, lp, lane, acc_rel, span); break;
+                    case 3: run_multi_store<3, UNR>(slots, nval, lp, lane, acc_rel, span); break;
+                    case 4: run_multi_store<4, UNR>(slots, nval, lp, lane, acc_rel, span); break;
+                    case 5: run_multi_store<5, UNR>(slots, nval, lp, lane, acc_rel, span); break;
+                    case 6: run_multi_store<6, UNR>(slots, nval, lp, lane, acc_rel, span); break;
+                    case 7: run_multi_store<7, UNR>(slots, nval, lp, lane, acc_rel, span); break;
+                    default: run_multi_store<8, UNR>(slots, nval, lp, lane, acc_rel, span); break;
                     }
                 } else {
                     unsigned mask = 0u;
@@ -763,11 +766,11 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                     __syncwarp();
                     if (span <= 8) {
                         const double acc =
-                            run_slots<8>(slots, nval, V.tprofile + (lane & 7), lane);
+                            run_slots<8, UNR>(slots, nval, V.tprofile + (lane & 7), lane);
                         if (lane < 8 && lane < span) acc_rel[lane] += acc;
                     } else if (span <= 16) {
                         const double acc =
-                            run_slots<16>(slots, nval, V.tprofile + (lane & 15), lane);
+                            run_slots<16, UNR>(slots, nval, V.tprofile + (lane & 15), lane);
                         if (lane < 16 && lane < span) acc_rel[lane] += acc;
                     } else {
                         // generic: one pass of 32 outputs at a time with restaged lane masks
@@ -782,7 +785,7 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                                 if (!__any_sync(0xffffffffu, mask != 0u)) continue;
                             }
                             const double acc =
-                                run_slots<32>(slots, nval, V.tprofile + x0 + lane, lane);
+                                run_slots<32, UNR>(slots, nval, V.tprofile + x0 + lane, lane);
                             if (x0 + lane < span) acc_rel[x0 + lane] += acc;
                         }
                     }
@@ -1016,10 +1019,15 @@ int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
         const size_t csmem = smem + sizeof(double) * 8 * kChunkTile;
         // more than 48 KB of dynamic shared memory needs the per-device opt-in (not the case
         // for 512-output tiles unless the Doppler grid is huge)
+        // outputs a line can cover: 2*cutoff/wnstep (+1); three or more passes of 32 -> wide variant
+        const bool wide = V.tstride > 0 && V.cut_fine != 0x7fffffff &&
+                          2LL * V.cut_fine / V.tstride >= 96;
+        auto narrow_k = accumulate_chunks_kernel<PB200_CHUNK_MINBLOCKS, PB200_CHUNK_UNROLL>;
+        auto wide_k = accumulate_chunks_kernel<3, 16>;
         if (csmem > 48 * 1024)
-            PB_CUDA(cudaFuncSetAttribute(accumulate_chunks_kernel,
+            PB_CUDA(cudaFuncSetAttribute(wide ? wide_k : narrow_k,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-        accumulate_chunks_kernel<<<grid, 256, csmem, st>>>(
+        (wide ? wide_k : narrow_k)<<<grid, 256, csmem, st>>>(
             V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
     } else if (mode == kLinterp)
         accumulate_kernel<kLinterp><<<grid, 256, smem, st>>>(
