@@ -156,17 +156,22 @@ def read_tli_file(tli_file, wn_low, wn_high, log=None):
     gf = np.empty(nlt, np.double)
     isoid = np.empty(nlt, np.short)
     pos = 0
-    with open(tli_file, "rb") as f:
-        for first, n in segments:
-            wn[pos:pos + n] = wn_all[first:first + n]
-            f.seek(init_iso + first * pc.sreclen)
-            isoid[pos:pos + n] = np.fromfile(f, np.short, n)
-            f.seek(init_el + first * pc.dreclen)
-            elow[pos:pos + n] = np.fromfile(f, np.double, n)
-            f.seek(init_gf + first * pc.dreclen)
-            gf[pos:pos + n] = np.fromfile(f, np.double, n)
-            pos += n
     del wn_all
+
+    def read_into(f, offset, dest):
+        # straight into the destination slice: no temporary array, no second pass
+        f.seek(offset)
+        got = f.readinto(memoryview(dest).cast('B'))
+        if got != dest.nbytes:
+            raise ValueError("TLI file truncated while reading the line records")
+
+    with open(tli_file, "rb", buffering=0) as f:
+        for first, n in segments:
+            read_into(f, init_wl + first * pc.dreclen, wn[pos:pos + n])
+            read_into(f, init_iso + first * pc.sreclen, isoid[pos:pos + n])
+            read_into(f, init_el + first * pc.dreclen, elow[pos:pos + n])
+            read_into(f, init_gf + first * pc.dreclen, gf[pos:pos + n])
+            pos += n
     if log is not None:
         log.msg(f'There are {n_transitions:,d} line transitions in TLI file.', indent=2)
     return databases, wn, gf, elow, isoid
