@@ -13,6 +13,9 @@ SOURCES = ["engine.cu", "lbl_kernels.cu", "voigt.cu", "microbench.cu",
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
+    # no implicit FMA contraction in device code: every fused multiply-add is an explicit fma()
+    # (the hot gathers), everything else rounds like the reference's C expressions
+    "-fmad=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math",
     "--shared",
 ]

@@ -911,10 +911,11 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         }
     }
     const int ntp = (int)tp_temp.size();
-    // the strengths kernel multiplies by 1/T and 1/Z (IEEE reciprocals taken here, once)
-    std::vector<double> tp_inv_t(tp_temp.size()), tp_inv_z(tp_isoz.size());
-    for (size_t i = 0; i < tp_temp.size(); i++) tp_inv_t[i] = 1.0 / tp_temp[i];
-    for (size_t i = 0; i < tp_isoz.size(); i++) tp_inv_z[i] = 1.0 / tp_isoz[i];
+    // the strengths kernel forms the exactly rounded quotients x/T and x/Z from {T, RN(1/T)}
+    // and {Z, RN(1/Z)} (quotient_rn); the reciprocals are taken here, once
+    std::vector<double2> tp_t(tp_temp.size()), tp_z(tp_isoz.size());
+    for (size_t i = 0; i < tp_temp.size(); i++) tp_t[i] = make_double2(tp_temp[i], 1.0 / tp_temp[i]);
+    for (size_t i = 0; i < tp_isoz.size(); i++) tp_z[i] = make_double2(tp_isoz[i], 1.0 / tp_isoz[i]);
 
     // Accumulate mode per unit: constant-step outputs read the output-stride table when the
     // unit's dynamic stride ofactor*scale equals the table's stride (always true when
@@ -925,9 +926,21 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
     const bool allow_transposed = !(force && std::strcmp(force, "strided") == 0);
     if (!resolution && allow_transposed) {
         const int stride = (int)std::llround(wnstep / ownstep);
+        // The output-owned kernel packs the table offset into 32 bits and the chunk kernel into
+        // 31: a larger output-stride table (> 34 GB) falls back to the strided gather, which
+        // uses 64-bit addresses.  PB200_PACK_LIMIT lowers the limit (tests force the fallback).
+        long long pack_limit = 0xffffffffLL;
+        {
+            const char *env = std::getenv("PB200_PACK_LIMIT");
+            if (env && std::atoll(env) > 0) pack_limit = std::min(pack_limit, std::atoll(env));
+        }
+        // the transposed table is at most stride-1 samples per profile longer than the original
+        const long long tlen_bound =
+            e->profile_len + (long long)e->nlor * e->ndop * (long long)std::max(stride, 1) + 256;
+        const bool fits = tlen_bound + nwave + 64 < pack_limit;
         bool any = false;
         for (int u = 0; u < n_units; u++)
-            if (stride >= 1 && (long long)units[u].ofactor * units[u].scale == stride) {
+            if (fits && stride >= 1 && (long long)units[u].ofactor * units[u].scale == stride) {
                 unit_mode[u] = kModeTransposed;
                 any = true;
             }
@@ -957,6 +970,12 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         tp_chunk = (int)std::min<size_t>((size_t)ntp, std::max<size_t>(1, budget / per_tp));
     }
     if (tp_chunk > 65535) tp_chunk = 65535;
+    {
+        // PB200_TP_CHUNK=<n> forces the strengths passes into chunks of n (the GPU tests compare
+        // a chunked batch with an unchunked one bit for bit)
+        const char *env = std::getenv("PB200_TP_CHUNK");
+        if (env && std::atoi(env) >= 1) tp_chunk = std::min(tp_chunk, std::atoi(env));
+    }
 
     rc = e->d_ksum.alloc((size_t)tp_chunk * (size_t)std::max<int64_t>(e->ngroups, 1));
     if (!rc) rc = e->d_kmax.alloc((size_t)tp_chunk * nrows);
@@ -964,8 +983,8 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
     auto align16 = [](size_t n) { return (n + 15) & ~(size_t)15; };
     const size_t off_row = 0;
     const size_t off_invt = off_row + align16(sizeof(int) * niso);
-    const size_t off_invz = off_invt + align16(sizeof(double) * tp_chunk);
-    const size_t off_units = off_invz + align16(sizeof(double) * (size_t)tp_chunk * niso);
+    const size_t off_invz = off_invt + align16(sizeof(double2) * tp_chunk);
+    const size_t off_units = off_invz + align16(sizeof(double2) * (size_t)tp_chunk * niso);
     const size_t off_iso = off_units + align16(sizeof(UnitParams) * (size_t)n_units);
     const size_t stage_bytes = off_iso + align16(sizeof(IsoUnit) * (size_t)n_units * niso);
     if (!rc) rc = e->d_stage.alloc(stage_bytes);
@@ -1014,6 +1033,31 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         const char *env = std::getenv("PB200_ACC_KERNEL");
         if (env && std::strcmp(env, "owner") == 0) chunked = 0;
     }
+    // Units per accumulate launch: grid.y is limited to 65535, and the partial spectra of a
+    // split launch (ksplit > 1) to 1 GiB; the scratch is sized ONCE per batch for the largest
+    // launch (growing it between launches would free a buffer that queued kernels still use).
+    size_t max_nu = 65535;
+    if (ksplit > 1) {
+        const size_t per_unit = sizeof(double) * (size_t)nrows * ksplit * (size_t)nwave;
+        max_nu = std::max<size_t>(1, std::min<size_t>(max_nu, ((size_t)1 << 30) / per_unit));
+        rc = e->d_partial.alloc(std::min<size_t>((size_t)n_units, max_nu) * nrows * ksplit *
+                                (size_t)nwave);
+        if (rc) return rc;
+    }
+    {
+        const char *env = std::getenv("PB200_MAX_UNITS_PER_LAUNCH");  // tests: force launch splits
+        if (env && std::atoi(env) >= 1) max_nu = std::min<size_t>(max_nu, (size_t)std::atoi(env));
+    }
+    // The half-batch D2H overlap below needs page-locked memory: cudaMemcpyAsync into pageable
+    // memory blocks the host until the copy is done, which would delay the second half.
+    bool out_pinned = false;
+    if (out_host) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, out_host) == cudaSuccess)
+            out_pinned = attr.type == cudaMemoryTypeHost;
+        else
+            cudaGetLastError();
+    }
     float ms_strengths = 0.f, ms_accum = 0.f;
     size_t copied_rows = 0, split_after = 0;  // rows already sent to the host by the copy stream
     // order units by strengths pass
@@ -1042,15 +1086,15 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
             }
         }
         std::memcpy(e->h_stage + off_row, iso_row.data(), sizeof(int) * niso);
-        std::memcpy(e->h_stage + off_invt, tp_inv_t.data() + tp0, sizeof(double) * ntc);
-        std::memcpy(e->h_stage + off_invz, tp_inv_z.data() + (size_t)tp0 * niso,
-                    sizeof(double) * ntc * niso);
+        std::memcpy(e->h_stage + off_invt, tp_t.data() + tp0, sizeof(double2) * ntc);
+        std::memcpy(e->h_stage + off_invz, tp_z.data() + (size_t)tp0 * niso,
+                    sizeof(double2) * ntc * niso);
         std::memcpy(e->h_stage + off_units, cu.data(), sizeof(UnitParams) * cu.size());
         std::memcpy(e->h_stage + off_iso, ci.data(), sizeof(IsoUnit) * ci.size());
         PB_CUDA(cudaMemcpyAsync(e->d_stage.p, e->h_stage, stage_bytes, cudaMemcpyHostToDevice, st));
         const int *p_iso_row = reinterpret_cast<const int *>(e->d_stage.p + off_row);
-        const double *p_inv_t = reinterpret_cast<const double *>(e->d_stage.p + off_invt);
-        const double *p_inv_z = reinterpret_cast<const double *>(e->d_stage.p + off_invz);
+        const double2 *p_inv_t = reinterpret_cast<const double2 *>(e->d_stage.p + off_invt);
+        const double2 *p_inv_z = reinterpret_cast<const double2 *>(e->d_stage.p + off_invz);
         const UnitParams *p_units = reinterpret_cast<const UnitParams *>(e->d_stage.p + off_units);
         const IsoUnit *p_iso_units = reinterpret_cast<const IsoUnit *>(e->d_stage.p + off_iso);
         PB_CUDA(cudaMemsetAsync(e->d_kmax.p, 0, sizeof(unsigned long long) * ntc * nrows, st));
@@ -1063,11 +1107,12 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         // one launch per run of equal mode; grid.y is limited to 65535 units per launch
         for (size_t u0 = 0; u0 < cu.size();) {
             size_t u1 = u0;
-            while (u1 < cu.size() && cmode[u1] == cmode[u0] && u1 - u0 < 65535) u1++;
+            while (u1 < cu.size() && cmode[u1] == cmode[u0] && u1 - u0 < max_nu) u1++;
             // Host output: run the first half of the batch on its own, so that its rows travel
             // to the host (copy stream) while the second half is computed.  Only when the
             // first half is exactly the rows [0, half) of the caller's array.
-            if (out_host && !counters && u0 == 0 && tp0 == 0 && ntc == ntp && u1 == cu.size() &&
+            if (out_host && out_pinned && !counters && u0 == 0 && tp0 == 0 && ntc == ntp &&
+                u1 == cu.size() &&
                 copied_rows == 0 && u1 >= 16) {
                 const size_t half = u1 / 2;
                 bool prefix = true;
@@ -1079,8 +1124,6 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
                 }
             }
             const int nu = (int)(u1 - u0);
-            rc = e->d_partial.alloc(ksplit > 1 ? (size_t)nu * nrows * ksplit * (size_t)nwave : 0);
-            if (rc) return rc;
             rc = launch_accumulate(st, V, nu, p_units + u0, p_iso_units + u0 * niso,
                                    p_iso_row, e->d_ksum.p, e->d_kmax.p, nrows, ethresh,
                                    cutoff, cmode[u0], d_out, ksplit, e->d_partial.p, chunked);

@@ -99,18 +99,19 @@ __device__ __forceinline__ bool prepare_group(const StaticView &V, const UnitPar
 
 // ---------------------------------------------------------------------------------------
 // Kernel 1: line strengths per (T, Z) pass, summed per co-add group, and the per-row maximum.
-// Divisions by T and Z are multiplications by reciprocals rounded once on the host: what the
-// reference's own -O3 -ffast-math build does; <= 1 ulp per factor (1e-15 on the strength).
+// The divisions by T and Z are correctly rounded IEEE quotients (quotient_rn: host-rounded
+// reciprocal + two FMA residual corrections, bit-identical to a/b), so the strength that
+// feeds the `k < ethresh*kmax` predicate equals the strict-IEEE evaluation of the reference's
+// expression by construction, not only within an ulp.
 #ifndef PB200_STR_MINBLOCKS
 #define PB200_STR_MINBLOCKS 4
 #endif
 // SIGCTE*ratio*gf * exp(-EXPCTE*elow/T) * (1-exp(-EXPCTE*wn/T)) / Z   (_extcoeff.c:219-224)
-// with the divisions by T and Z as multiplications by the host-rounded reciprocals.
 __device__ __forceinline__ double line_strength(double w, double elow, double gf, double pref,
-                                                double inv_t, double inv_z) {
-    const double pop = exp(dmul(dmul(-kExpCte, elow), inv_t));
-    const double ind = dsub(1.0, exp(dmul(dmul(-kExpCte, w), inv_t)));
-    return dmul(dmul(dmul(dmul(pref, gf), pop), ind), inv_z);
+                                                double t, double inv_t, double z, double inv_z) {
+    const double pop = exp(quotient_rn(dmul(-kExpCte, elow), t, inv_t));
+    const double ind = dsub(1.0, exp(quotient_rn(dmul(-kExpCte, w), t, inv_t)));
+    return quotient_rn(dmul(dmul(dmul(pref, gf), pop), ind), z, inv_z);
 }
 
 // Kernel 1.  One thread per in-window LINE, kStrTemps temperature passes per thread:
@@ -134,7 +135,7 @@ constexpr int kStrTemps = PB200_STR_TEMPS;
 __global__ void __launch_bounds__(256, PB200_STR_MINBLOCKS)
 strengths_kernel(StaticView V, const int *__restrict__ l_group,
                  const unsigned short *__restrict__ l_iso, long long nlines, int ntp,
-                 const double *__restrict__ tp_inv_t, const double *__restrict__ tp_inv_z,
+                 const double2 *__restrict__ tp_t, const double2 *__restrict__ tp_z,
                  const int *__restrict__ iso_row, int nrows, double *__restrict__ ksum,
                  unsigned long long *__restrict__ kmax) {
     const long long ln = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -165,15 +166,17 @@ strengths_kernel(StaticView V, const int *__restrict__ l_group,
 
     const int t0 = blockIdx.y * kStrTemps, t1 = min(ntp, t0 + kStrTemps);
     unsigned long long mine = 0ull;  // lane j keeps the warp maximum of pass t0 + j
-    double nx_inv_t = tp_inv_t[t0], nx_inv_z = tp_inv_z[(size_t)t0 * V.niso + iso];
+    // {T, RN(1/T)} and {Z, RN(1/Z)} of a pass travel as one 16-byte word each
+    double2 nx_t = tp_t[t0], nx_z = tp_z[(size_t)t0 * V.niso + iso];
 #pragma unroll 1
     for (int tp = t0; tp < t1; tp++) {
-        const double inv_t = nx_inv_t, inv_z = nx_inv_z;
+        const double2 ct = nx_t, cz = nx_z;
         if (tp + 1 < t1) {  // next pass's scalars, requested one pass ahead
-            nx_inv_t = tp_inv_t[tp + 1];
-            nx_inv_z = tp_inv_z[(size_t)(tp + 1) * V.niso + iso];
+            nx_t = tp_t[tp + 1];
+            nx_z = tp_z[(size_t)(tp + 1) * V.niso + iso];
         }
-        const double kl = row >= 0 ? line_strength(w, elow, gf, pref, inv_t, inv_z) : 0.0;
+        const double kl =
+            row >= 0 ? line_strength(w, elow, gf, pref, ct.x, ct.y, cz.x, cz.y) : 0.0;
         double k = kl;
         for (int jm = 1; jm <= maxm; jm++) {
             const double v = __shfl_down_sync(0xffffffffu, kl, jm);
@@ -181,7 +184,8 @@ strengths_kernel(StaticView V, const int *__restrict__ l_group,
         }
         if (head) {
             for (long long m = warp_end; m < (long long)ext_end; m++)
-                k = dadd(k, line_strength(V.l_wn[m], V.l_elow[m], V.l_gf[m], pref, inv_t, inv_z));
+                k = dadd(k, line_strength(V.l_wn[m], V.l_elow[m], V.l_gf[m], pref, ct.x, ct.y,
+                                          cz.x, cz.y));
             ksum[(size_t)tp * V.ngroups + code] = k;
         }
         if (nrows == 1) {
@@ -982,14 +986,14 @@ interp_ec_kernel(double *__restrict__ ext, const double *__restrict__ table,
 
 // ---------------------------------------------------------------------------------------
 // Launch wrappers
-int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double *tp_inv_t,
-                     const double *tp_inv_z, const int *iso_row, int nrows, double *ksum,
+int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double2 *tp_t,
+                     const double2 *tp_z, const int *iso_row, int nrows, double *ksum,
                      unsigned long long *kmax, const int *l_group,
                      const unsigned short *l_iso, long long nlines) {
     if (V.ngroups == 0 || ntp == 0 || nlines == 0) return 0;
     dim3 grid((unsigned)((nlines + 255) / 256), (unsigned)((ntp + kStrTemps - 1) / kStrTemps));
-    strengths_kernel<<<grid, 256, 0, st>>>(V, l_group, l_iso, nlines, ntp, tp_inv_t, tp_inv_z,
-                                           iso_row, nrows, ksum, kmax);
+    strengths_kernel<<<grid, 256, 0, st>>>(V, l_group, l_iso, nlines, ntp, tp_t, tp_z, iso_row,
+                                           nrows, ksum, kmax);
     PB_CUDA(cudaGetLastError());
     return 0;
 }

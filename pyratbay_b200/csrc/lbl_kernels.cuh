@@ -4,9 +4,9 @@
 
 namespace pb200 {
 
-// tp_inv_t[ntp] = 1/T and tp_inv_z[ntp, niso] = 1/Z of every strengths pass (host-rounded).
-int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double *tp_inv_t,
-                     const double *tp_inv_z, const int *iso_row, int nrows, double *ksum,
+// tp_t[ntp] = {T, RN(1/T)} and tp_z[ntp, niso] = {Z, RN(1/Z)} of every strengths pass.
+int launch_strengths(cudaStream_t st, const StaticView &V, int ntp, const double2 *tp_t,
+                     const double2 *tp_z, const int *iso_row, int nrows, double *ksum,
                      unsigned long long *kmax, const int *l_group,
                      const unsigned short *l_iso, long long nlines);
 

@@ -12,9 +12,13 @@ from . import parallel
 from ._mem import pinned_zeros
 
 
-def compute_opacity(pyrat):
+def compute_opacity(pyrat, write=True, host='rank0', nchunks=4):
     """Compute the cross-section table (cm2 molecule-1) over the (T, p, wn) grid and write
-    it to `ex.sampled_cs[0]` (pyrat/extinction.py:14-126)."""
+    it to `ex.sampled_cs[0]` (pyrat/extinction.py:14-126).
+
+    write  : write the .npz file (rank 0); False leaves the table in memory only.
+    host   : which ranks copy the table to host memory (`ex.etable`): 'rank0', 'all', 'none'.
+    nchunks: pieces a rank's rows are computed and all-gathered in (world > 1)."""
     ex = pyrat.ex
     spec = pyrat.spec
     log = pyrat.log
@@ -70,36 +74,58 @@ def compute_opacity(pyrat):
     ex.nlayers = pyrat.atm.nlayers
 
     log.msg("Calculate cross-sections.", indent=2)
-    ex.etable = pinned_zeros((ex.ntemp, ex.nlayers, ex.nwave))
-
-    # One batched GPU call per rank over its share of the (T,p) indices (:108-119)
+    # One process per GPU.  Every rank computes its share of the (T,p) units (:108-119, where
+    # the reference forks) straight into device memory; finished chunks are all-gathered over
+    # NCCL while the next chunk is computed, so the whole table ends up in the HBM of every
+    # rank (`ex.etable_dev`, what a device-side consumer such as Line_Sample reads) and is
+    # copied to the host (`ex.etable`, the array the reference fills) only where it is written.
+    import torch
     n_units = ex.ntemp * ex.nlayers
     rank, world = parallel.rank_world()
-    if world == 1:
-        extinction(pyrat, np.arange(n_units), grid=True, add=False)
-    else:
+    cost = None
+    if world > 1:
         # deal units to ranks by estimated cost (wide, high-pressure profiles cost more)
         idx = np.arange(n_units)
         cost = parallel.unit_costs(
             pyrat.voigt, spec, pyrat.atm, lbl.iso_atm_index, lbl.iso_mass,
             ex.temp[idx // ex.nlayers], ex.press[idx % ex.nlayers],
             pyrat.atm.vmr[idx % ex.nlayers])
-        mine = parallel.partition_units(n_units, rank, world, cost)
-        extinction(pyrat, mine, grid=True, add=False)
-        flat = ex.etable.reshape(n_units, ex.nwave)
-        parallel.assemble_rows(flat, mine, device=pyrat.device, cost=cost)
+    owners = parallel.unit_owners(n_units, world, cost, equal_counts=True)
+    asm = getattr(ex, '_assembler', None)
+    if asm is None or (asm.n_units, asm.nwave, asm.world) != (n_units, ex.nwave, world) \
+            or any(not np.array_equal(a, b) for a, b in zip(asm.owners, owners)):
+        ex._assembler = None                        # release the old buffers first
+        asm = ex._assembler = parallel.TableAssembler(
+            n_units, ex.nwave, owners, rank, device=pyrat.device, nchunks=nchunks)
+    ex.timing = {'strengths_ms': 0.0, 'accumulate_ms': 0.0, 'total_ms': 0.0}
+    for c, units, ptr in asm.chunks():
+        if len(units):
+            extinction(pyrat, units, grid=True, add=False, out_device_ptr=ptr)
+            for key in ex.timing:
+                ex.timing[key] += float(pyrat.last_timing[key])
+        asm.publish(c)
+    table = asm.finish()
+    ex.etable_dev = table.view(ex.ntemp, ex.nlayers, ex.nwave)
 
-    if rank == 0:
+    if write and host == 'none':
+        host = 'rank0'
+    if host == 'all' or (host == 'rank0' and rank == 0):
+        if getattr(ex, 'etable', None) is None or ex.etable.shape != tuple(ex.etable_dev.shape):
+            ex.etable = pinned_zeros(ex.etable_dev.shape)
+        torch.from_numpy(ex.etable).copy_(ex.etable_dev)     # one D2H into pinned memory
+    if write and rank == 0:
         io.write_opacity(cs_file, ex.species, ex.temp, ex.press, ex.wn, ex.etable)
         log.head(f"Cross-section table written to file: '{cs_file}'.", indent=2)
 
 
-def extinction(pyrat, indices, grid=False, add=False, skip_mol=[]):
+def extinction(pyrat, indices, grid=False, add=False, skip_mol=[], out_device_ptr=None):
     """Extinction coefficient for atmospheric layers or table indices
     (pyrat/extinction.py:129-215).
 
     grid=True : index = itemp*nlayers + ilayer; stores into pyrat.ex.etable[itemp, ilayer].
     add=True  : co-added extinction (cm-1) stored into lbl.ec[ilayer].
+    out_device_ptr : device address of a [len(indices), nrows, nwave] float64 buffer; the rows
+                are left there (in `indices` order) and nothing is stored on the host.
     otherwise : returns the per-species cross section (cm2 molecule-1) of the FIRST index
                 only, as the reference does (:214-215).
     """
@@ -137,6 +163,12 @@ def extinction(pyrat, indices, grid=False, add=False, skip_mol=[]):
         log.msg(f"Calculating extinction at {len(indices)} layer(s).", indent=2)
 
     nrows = 1 if add else lbl.nspec
+    if out_device_ptr is not None:
+        pyrat.engine.extinction_batch(
+            temp, density, iso_pf, iso_mol_indices, lbl.nspec, lbl.ethresh, add, interpolate,
+            out_device_ptr=out_device_ptr)
+        pyrat.last_timing = pyrat.engine.last_timing()
+        return None
     # Write straight into the caller-visible array when the batch covers it in order.
     out = None
     in_order = np.array_equal(indices, np.arange(len(indices)))

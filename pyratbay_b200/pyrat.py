@@ -85,9 +85,10 @@ class Pyrat:
                 dmin=inputs.voigt_dmin, dmax=inputs.voigt_dmax, lmin=inputs.voigt_lmin,
                 lmax=inputs.voigt_lmax, tmin=inputs.tmin, tmax=inputs.tmax, log=self.log)
 
-    def compute_opacity(self):
-        """Cross-section table build (pyrat_obj.py:121-126)."""
-        ex_mod.compute_opacity(self)
+    def compute_opacity(self, **kwargs):
+        """Cross-section table build (pyrat_obj.py:121-126); keyword options of
+        extinction.compute_opacity (write, host, nchunks)."""
+        ex_mod.compute_opacity(self, **kwargs)
 
     def calc_lbl_extinction(self, temp=None, vmr=None, skip_mol=[]):
         """The LBL part of Pyrat.run's extinction stage (pyrat_obj.py:203-206): update the

@@ -40,6 +40,47 @@ def forward_model_workload(nlines=1_000_000, nlayers=81, wl_low_um=0.5, wl_high_
               f"{wl_low_um}-{wl_high_um} um forward-model extinction"))
 
 
+def table_workload(nlines=100_000_000, ntemp=20, nlayers=51, nwave=100_000, wl_low_um=0.3,
+                   wl_high_um=30.0, tmin=300.0, tstep=150.0, ptop=1e-6, pbottom=100.0,
+                   window=None):
+    """configs[2]: cross-section table of a synthetic ExoMol-scale H2O list over
+    ntemp x nlayers (T,p) units and a constant-step grid of `nwave` samples (add=0).
+
+    The grid is defined by round numbers so that every arm builds the identical one:
+    wnlow = 1/wl_high, wnstep = (1/wl_low - 1/wl_high)/nwave rounded to 2 digits, wnosamp from
+    the reference's 4e-4 rule (spectrum.py:187-190).  `window` = (first, count) restricts the
+    workload to that slice of the output grid with the same line density (the bounded CPU
+    sample of bench.py): lines ~ U over the sub-window, nlines scaled by its share.
+
+    Returns a namespace with the `Pyrat` input keys (`inputs`), the atmosphere, the database
+    header and `make_lines()` -> (wn, elow, gf, iso_id, counts)."""
+    from .spectrum import _HCN
+    wnlow = 1.0 / (wl_high_um * pc.um)
+    wnstep = float(f"{(1.0 / (wl_low_um * pc.um) - wnlow) / nwave:.2g}")
+    wnosamp = int(_HCN[wnstep / _HCN <= 0.0004][0])
+    first, count = (0, nwave) if window is None else window
+    lo = wnlow + first * wnstep
+    hi = lo + (count - 0.5) * wnstep                 # int((hi-lo)/wnstep) + 1 == count
+    nlines_w = int(round(nlines * count / nwave))
+    tmax = tmin + (ntemp - 1) * tstep
+    press = pa.pressure(ptop, pbottom, nlayers)
+    vmr = np.tile(np.asarray(UNIFORM_VMR), (nlayers, 1))
+    atm = pa.Atmosphere(press, np.full(nlayers, 1000.0), vmr, UNIFORM_SPECIES)
+    db = ptli.synthetic_h2o_database()
+    inputs = dict(wnlow=lo, wnhigh=hi, wnstep=wnstep, wnosamp=wnosamp, tmin=tmin, tmax=tmax,
+                  tstep=tstep, verb=0)
+    return SimpleNamespace(
+        inputs=inputs, atm=atm, db=db, nlines=nlines_w, ntemp=ntemp, nlayers=nlayers,
+        nwave=count, wnstep=wnstep, wnosamp=wnosamp, temps=tmin + tstep * np.arange(ntemp),
+        iso_atm_index=np.full(db.niso, UNIFORM_SPECIES.index('H2O'), int),
+        iso_mol_index=np.zeros(db.niso, int),
+        make_lines=lambda seed=0: ptli.synthetic_lines(nlines_w, lo, lo + (count - 1) * wnstep,
+                                                       seed=seed),
+        name=(f"synthetic {nlines:.0e}-line H2O, {ntemp} T ({tmin:g}-{tmax:g} K) x {nlayers} p "
+              f"({ptop:g}-{pbottom:g} bar) x {nwave} wn ({wl_low_um:g}-{wl_high_um:g} um, "
+              f"wnstep {wnstep:g} cm-1, wnosamp {wnosamp}) cross-section table, add=0"))
+
+
 def partition(db, temps):
     """Z_i(T) [len(T), niso] with the reference's interpolant (scipy slinear)."""
     import scipy.interpolate as sip

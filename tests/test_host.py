@@ -277,6 +277,52 @@ def test_table_assembly_across_two_ranks_gloo(tmp_path):
         assert np.array_equal(np.load(tmp_path / f"table_{r}.npy"), full)
 
 
+def _gloo_assembler_worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, helpers.ROOT)
+    from pyratbay_b200 import parallel
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
+                            world_size=world)
+    n_units, nwave = 23, 17                       # 12 + 11 units: slots padded to 12 rows
+    full = np.arange(n_units * nwave, dtype=np.double).reshape(n_units, nwave) ** 1.5
+    cost = 1.0 + (np.arange(n_units) % 5)
+    owners = parallel.unit_owners(n_units, world, cost, equal_counts=True)
+    asm = parallel.TableAssembler(n_units, nwave, owners, rank, device=None, nchunks=3)
+    seen = []
+    for c, units, _ptr in asm.chunks():           # "compute" this rank's rows chunk by chunk
+        lo = asm.bounds[c]
+        asm.local[lo:lo + len(units)] = torch.from_numpy(full[units])
+        seen.append(units)
+        asm.publish(c)
+    table = asm.finish().numpy()
+    assert np.array_equal(np.concatenate(seen), owners[rank])
+    np.save(os.path.join(tmp, f"asm_{rank}.npy"), table)
+    dist.destroy_process_group()
+
+
+def test_chunked_device_style_assembly_two_ranks_gloo(tmp_path):
+    """TableAssembler (the product path of compute_opacity at N > 1) with uneven row counts
+    and three overlapped chunks, on CPU tensors over gloo."""
+    import torch.multiprocessing as tmp_mp
+    port = 31500 + os.getpid() % 2000
+    tmp_mp.spawn(_gloo_assembler_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    full = np.arange(23 * 17, dtype=np.double).reshape(23, 17) ** 1.5
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / f"asm_{r}.npy"), full)
+
+
+def test_equal_count_partition():
+    from pyratbay_b200 import parallel
+    cost = np.random.default_rng(1).uniform(1, 30, 1020)
+    owners = parallel.unit_owners(1020, 8, cost, equal_counts=True)
+    assert sorted(np.concatenate(owners)) == list(range(1020))
+    assert max(len(o) for o in owners) == 128 and min(len(o) for o in owners) >= 124
+    loads = np.array([cost[o].sum() for o in owners])
+    assert loads.max() / loads.min() < 1.02
+    assert all(np.all(np.diff(o) > 0) for o in owners)
+
+
 def test_unit_costs_balance_table_partition():
     """Cost model used to deal (T,p) units to ranks: grows with pressure (wider profiles) and
     gives a far better balance than round-robin would on cost."""
