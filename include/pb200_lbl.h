@@ -147,6 +147,12 @@ int pb200_extinction_batch_dev(pb200_engine *e, int n_units, const double *unit_
 int pb200_engine_last_timing(const pb200_engine *e, double ms[5]);
 /* Kernel launches issued by this engine since creation. */
 int64_t pb200_engine_launch_count(const pb200_engine *e);
+
+/* (unit, isotope) pairs of the last batch that took the dense-convolution accumulate path
+ * (isotopes whose co-add groups fill >= 25 % of the fine grid, constant-step output grids;
+ * csrc/dense_kernels.cu).  0: every isotope went through the gather kernels.  Same results
+ * either way (_extcoeff.c:229-309); diagnostic only. */
+int64_t pb200_engine_dense_units(const pb200_engine *e);
 /* The engine's CUDA stream (cudaStream_t), so a caller can record its own events on it. */
 void *pb200_engine_stream(const pb200_engine *e);
 

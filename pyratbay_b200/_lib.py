@@ -22,6 +22,7 @@ EXPORTS = [
     "pb200_engine_get_profile", "pb200_engine_set_species", "pb200_engine_set_partition",
     "pb200_engine_set_lines", "pb200_engine_line_stats", "pb200_extinction_batch_host",
     "pb200_extinction_batch_dev", "pb200_engine_last_timing", "pb200_engine_launch_count",
+    "pb200_engine_dense_units",
     "pb200_interp_ec", "pb200_interp_ec_per_mol", "pb200_interp_ec_dev",
     "pb200_engine_stream", "pb200_bench_fp64", "pb200_bench_l2",
     "pb200_nearest_thresholds", "pb200_selftest_exact",
@@ -53,6 +54,8 @@ def load():
     lib.pb200_engine_profile_len.argtypes = [c_void_p]
     lib.pb200_engine_launch_count.restype = ctypes.c_int64
     lib.pb200_engine_launch_count.argtypes = [c_void_p]
+    lib.pb200_engine_dense_units.restype = ctypes.c_int64
+    lib.pb200_engine_dense_units.argtypes = [c_void_p]
     lib.pb200_engine_stream.restype = c_void_p
     lib.pb200_engine_stream.argtypes = [c_void_p]
     lib.pb200_engine_destroy.restype = None

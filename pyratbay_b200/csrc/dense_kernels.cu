@@ -1,0 +1,343 @@
+// dense_kernels.cu -- accumulate as a dense strided convolution (constant-step output grids).
+//
+// The gather kernels (lbl_kernels.cu) deliver one 8-byte profile sample from L1/L2 per FMA and
+// are bound by that delivery (L2->SM at 97 % in table mode, 11 % of the fp64 peak).  For an
+// isotope whose co-add groups occupy a large share of the fine grid the same sums are a dense
+// 1-D convolution with operand reuse in registers:
+//
+//   a group sits on ONE fine cell f = S*c + r (c: output cell, r: sub-cell offset, S = fine
+//   samples per output sample), no two groups of an isotope share a cell (_extcoeff.c:249-262),
+//   and it adds  k * P[half - r + S*(m - c)]  to output m for m - c in a window [DL(r), DH(r))
+//   that depends on r only (for one unit, isotope and Doppler sample).  With the strengths
+//   scattered to a dense array K[f] (zeros where there is no group):
+//
+//       out[m] = sum_r sum_c K[S*c + r] * W_r[m - c],   W_r[d] = P[half - r + S*d] inside the
+//                                                       window, 0 outside.
+//
+// A lane owns one r, a warp 32 consecutive r and kDenseJ consecutive outputs in registers; it
+// walks the cells c that reach its outputs, loading ONE K value and ONE new W value per cell
+// for kDenseJ FMAs (the W window slides through a statically rotated register file).  K and W
+// tiles are staged in shared memory per (32 r) block and shared by the CTA's 16 warps, the lanes
+// are summed with shuffles at the very end, one CTA owns its outputs: no atomics, fixed order.
+//
+// Discrete decisions stay those of the reference.  The window of a cell comes from the SAME
+// device functions the gather kernels use (group_prep.cuh: dynamic_range, output_range),
+// evaluated at a reference cell in the middle of the grid (the window is translation invariant
+// away from the grid ends; clipping at the ends equals "outputs that exist").  Two things depend
+// on the line's exact wavenumber and not only on its cell:
+//   * the Doppler sample (:278): groups ascend in wavenumber, so the cells of one Doppler
+//     sample are a contiguous segment; segment_bounds_kernel finds the boundaries with the
+//     reference's nearest search and the tiles of K are masked per segment;
+//   * the dynamic index idwn = trunc((w - own0)/dwnstep) (:275), which is (cell / ofactor) - 1
+//     instead of cell / ofactor for a line below the centre of a cell divisible by ofactor
+//     ("anomalous" cells; static per ofactor, anomaly_bits_kernel).  Their window is shifted by
+//     one dynamic sample; the at most two output samples by which it differs are added /
+//     removed explicitly per anomalous cell.
+// The host uses this path only when the windows are provably translation invariant
+// (engine.cu: frac(cutoff/dwnstep) not within 1e-6 of an integer, grid ends far away).
+#include "dense_kernels.cuh"
+#include "group_prep.cuh"
+
+#include <climits>
+
+namespace pb200 {
+
+namespace {
+constexpr int J = kDenseJ;
+constexpr int kKRows = kDenseTile + kDenseSpanMax + 2 * J;   // K tile rows (cells)
+constexpr int kWRows = kDenseSpanMax + 3 * J;                // W tile rows (output offsets)
+}  // namespace
+
+size_t dense_smem_bytes() {
+    return sizeof(double) * 32 * (kKRows + kWRows) + sizeof(unsigned) * kKRows +
+           sizeof(short4) * kDenseMaxStride;
+}
+
+__global__ void __launch_bounds__(256)
+anomaly_bits_kernel(StaticView V, long long gbeg, long long gend, UnitParams U,
+                    unsigned *__restrict__ bits, int *__restrict__ err) {
+    const long long g = gbeg + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= gend) return;
+    const int iown = V.g_iown[g];
+    const int idwn = dynamic_index(V, U, V.g_wn[g]);
+    const int idwn0 = U.fd_ofactor.div(iown);
+    if (idwn == idwn0) return;
+    if (idwn == idwn0 - 1 && iown - idwn0 * U.ofactor == 0)
+        atomicOr(&bits[iown >> 5], 1u << (iown & 31));
+    else
+        atomicExch(err, 2);
+}
+
+__global__ void __launch_bounds__(256)
+densify_kernel(StaticView V, long long gbeg, long long gend, const double *__restrict__ ks,
+               const unsigned long long *__restrict__ kmax_entry, double ethresh,
+               double *__restrict__ kd) {
+    const long long g = gbeg + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= gend) return;
+    const double kthr = dmul(ethresh, __longlong_as_double((long long)*kmax_entry));
+    const double k = ks[g];
+    if (k < kthr) return;  // :265
+    kd[V.g_iown[g]] = k;
+}
+
+__global__ void __launch_bounds__(256)
+segment_bounds_kernel(StaticView V, long long gbeg, long long gend, double adop,
+                      int *__restrict__ bounds) {
+    extern __shared__ double s_dop[];
+    for (int i = threadIdx.x; i < V.ndop; i += blockDim.x)
+        s_dop[i] = V.dop_thr ? V.dop_thr[i] : V.doppler[i];
+    __syncthreads();
+    const int last = (int)(V.onwn < 0x7fffffffLL ? V.onwn : 0x7fffffffLL);
+    for (int j = threadIdx.x; j <= V.ndop; j += blockDim.x) {
+        int b = 0;
+        if (j == V.ndop) {
+            b = last;
+        } else if (j > 0) {
+            // first group whose nearest Doppler sample (:278) is >= j (monotonic in wavenumber)
+            long long lo = gbeg, hi = gend;
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                const int idop =
+                    V.ndop >= 2 ? doppler_index(V, s_dop, dmul(adop, V.g_wn[mid])) : 0;
+                if (idop >= j) hi = mid; else lo = mid + 1;
+            }
+            b = lo < gend ? V.g_iown[lo] : last;
+        }
+        bounds[j] = b;
+    }
+}
+
+__global__ void __launch_bounds__(kDenseWarps * 32, 1)
+accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
+                        const IsoUnit *__restrict__ iso_units, int iso, int row, int nrows,
+                        const double *__restrict__ kd, const int *__restrict__ bounds,
+                        const unsigned *__restrict__ abits, long long abits_words, double cutoff,
+                        double *__restrict__ out, int *__restrict__ err) {
+    extern __shared__ double s_dyn[];
+    double (*Ks)[32] = reinterpret_cast<double (*)[32]>(s_dyn);   // [kKRows]: cell c_lo + t
+    double (*Ws)[32] = Ks + kKRows;                               // [kWRows]: offset w_lo + t
+    unsigned *As = reinterpret_cast<unsigned *>(Ws + kWRows);     // [kKRows] anomaly bits of a row
+    short4 *s_win = reinterpret_cast<short4 *>(As + kKRows);      // [S] windows per sub-cell offset
+    __shared__ int s_dmin, s_dmax;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const UnitParams U = units[blockIdx.y];
+    const IsoUnit I = iso_units[(size_t)blockIdx.y * V.niso + iso];
+    const int S = V.tstride;
+    const int ms = blockIdx.x * kDenseTile;
+    const int m_end = min(ms + kDenseTile, min(V.nwave, U.mcount));   // exclusive
+    if (ms >= m_end) return;
+    const int mw0 = ms + warp * J;
+    const unsigned *__restrict__ ab = abits + (long long)U.aslot * abits_words;
+
+    double acc[J];
+#pragma unroll
+    for (int x = 0; x < J; x++) acc[x] = 0.0;
+
+    // fine cells that can reach this tile (conservative: the unit-wide reach of the isotope)
+    const long long reach_cells = I.reach / S + 2;
+    const long long flo = max(0LL, ((long long)ms - reach_cells) * S);
+    const long long fhi = min(V.onwn, ((long long)m_end + reach_cells) * S);
+    const int c_ref = U.mcount >> 1;   // reference cell for the windows, far from both grid ends
+
+    for (int seg = 0; seg < V.ndop; seg++) {
+        const long long sa = bounds[seg], sb = bounds[seg + 1];   // cells of Doppler sample `seg`
+        if (sb <= sa || sb <= flo || sa >= fhi) continue;         // CTA-uniform
+        const ProfileSlot ps = load_slot(V.pslot + I.ilor * V.ndop + seg);
+        const int half = ps.half;
+        const double *__restrict__ prof = V.profile + ps.base;
+
+        // (1) window of every sub-cell offset: outputs m - c in [x, y) for a regular cell,
+        //     [z, w) for an anomalous one (only cells divisible by ofactor can be)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_dmin = INT_MAX;
+            s_dmax = INT_MIN;
+        }
+        __syncthreads();
+        for (int r = threadIdx.x; r < S; r += blockDim.x) {
+            const int iown = c_ref * S + r;
+            const int idwn0 = U.fd_ofactor.div(iown);
+            int jlo, jhi, mlo, mhi, alo, ahi;
+            dynamic_range(U, cutoff, half, iown, idwn0, &jlo, &jhi);
+            output_range(U, jlo, jhi, &mlo, &mhi);
+            alo = mlo;
+            ahi = mhi;
+            if (iown - idwn0 * U.ofactor == 0) {
+                dynamic_range(U, cutoff, half, iown, idwn0 - 1, &jlo, &jhi);
+                output_range(U, jlo, jhi, &alo, &ahi);
+            }
+            if (mhi <= mlo) mlo = mhi = c_ref;   // empty windows: keep the offsets small
+            if (ahi <= alo) alo = ahi = c_ref;
+            s_win[r] = make_short4((short)(mlo - c_ref), (short)(mhi - c_ref),
+                                   (short)(alo - c_ref), (short)(ahi - c_ref));
+            if (mhi > mlo || ahi > alo) {
+                const int lo = (mhi > mlo ? (ahi > alo ? min(mlo, alo) : mlo) : alo) - c_ref;
+                const int hi = (mhi > mlo ? (ahi > alo ? max(mhi, ahi) : mhi) : ahi) - c_ref;
+                atomicMin(&s_dmin, lo);
+                atomicMax(&s_dmax, hi);
+            }
+        }
+        __syncthreads();
+        const int dmin = s_dmin, dmax = s_dmax;   // a cell c reaches outputs c+dmin .. c+dmax-1
+        if (dmax <= dmin) continue;
+        if (dmax - dmin > kDenseSpanMax || dmin < -30000 || dmax > 30000) {
+            if (threadIdx.x == 0) atomicExch(err, 1);   // the host sizes batches so this cannot happen
+            continue;
+        }
+
+        const int c_lo = ms - (dmax - 1);             // first cell that reaches the tile
+        const int w_lo = dmin - 2 * J;                // first offset held in Ws
+        const int nsteps = J + (dmax - dmin) - 1;     // cells that reach one warp's outputs
+        const int niter = (nsteps + J - 1) / J;
+        const int krows = kDenseTile - J + niter * J;
+        const int wrows = dmax + J - w_lo;
+        const int nrb = (S + 31) >> 5;
+
+        for (int rb = 0; rb < nrb; rb++) {
+            const int r = rb * 32 + lane;
+            const bool active = r < S;
+            const short4 win = active ? s_win[r] : make_short4(0, 0, 0, 0);
+            __syncthreads();   // the previous block's tiles are fully consumed
+
+            // (2) W tile: the unit's profile on the sub-cell offsets of this block, zero outside
+            //     each offset's window.  Reference layout: consecutive r are consecutive samples.
+            for (int t = warp; t < wrows; t += kDenseWarps) {
+                const int d = w_lo + t;
+                double v = 0.0;
+                if (active && d >= win.x && d < win.y)
+                    v = dmul(prof[(long long)half - r + (long long)S * d], I.dens);
+                Ws[t][lane] = v;
+            }
+            // (3) K tile, masked to the Doppler segment, and the anomaly bits of its rows
+            for (int t = warp; t < krows; t += kDenseWarps) {
+                const int c = c_lo + t;
+                const long long cell0 = (long long)c * S + rb * 32;
+                const long long cell = cell0 + lane;
+                double v = 0.0;
+                if (active && c >= 0 && cell >= sa && cell < sb) v = kd[cell];
+                Ks[t][lane] = v;
+                if (lane == 0) {
+                    unsigned bits = 0u;
+                    if (c >= 0 && cell0 < V.onwn) {
+                        const long long wi = cell0 >> 5;
+                        bits = __funnelshift_r(ab[wi], ab[wi + 1], (unsigned)(cell0 & 31));
+                    }
+                    As[t] = bits;
+                }
+            }
+            __syncthreads();
+
+            // (4) the convolution.  At cell c_start + n output x of the warp needs offset
+            //     (dmax-1) + x - n; the window registers rotate statically: w[(x - i) mod J].
+            {
+                double w[J];
+#pragma unroll
+                for (int x = 1; x < J; x++) w[x] = Ws[(dmax - 1 + x) - w_lo][lane];
+                w[0] = 0.0;
+                int krow = warp * J;
+                int wrow = (dmax - 1) - w_lo;
+                for (int it = 0; it < niter; it++) {
+#pragma unroll
+                    for (int i = 0; i < J; i++) {
+                        const double kv = Ks[krow + i][lane];
+                        w[(J - i) % J] = Ws[wrow - i][lane];
+#pragma unroll
+                        for (int x = 0; x < J; x++)
+                            acc[x] = fma(kv, w[(x - i + J) % J], acc[x]);
+                    }
+                    krow += J;
+                    wrow -= J;
+                }
+            }
+
+            // (5) anomalous cells of this block: add the samples their window has and the
+            //     regular one lacks, remove the opposite (at most one output at either end).
+            if (active && (win.z != win.x || win.w != win.y)) {
+#pragma unroll 1
+                for (int part = 0; part < 2; part++) {
+                    const int a = part ? min(win.y, win.w) : min(win.x, win.z);
+                    const int b = part ? max(win.y, win.w) : max(win.x, win.z);
+#pragma unroll 1
+                    for (int d = a; d < b; d++) {
+                        const bool in_n = d >= win.x && d < win.y;
+                        const bool in_a = d >= win.z && d < win.w;
+                        if (in_n == in_a) continue;
+                        const long long pi = (long long)half - r + (long long)S * d;
+                        if (pi < 0 || pi > 2LL * half) continue;
+                        double pv = dmul(prof[pi], I.dens);
+                        if (in_n) pv = -pv;
+                        const int t0 = warp * J + (dmax - 1) - d;   // K row of output 0's cell
+#pragma unroll
+                        for (int x = 0; x < J; x++)
+                            if ((As[t0 + x] >> lane) & 1u) acc[x] = fma(Ks[t0 + x][lane], pv, acc[x]);
+                    }
+                }
+            }
+        }
+    }
+
+    // (6) sum the 32 sub-cell offsets of a warp and add to the output row (the gather kernels
+    //     have written it: other isotopes, or zeros)
+    double mine = 0.0;
+#pragma unroll
+    for (int x = 0; x < J; x++) {
+        double v = acc[x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == x) mine = v;
+    }
+    if (lane < J && mw0 + lane < m_end) {
+        double *dst = out + ((size_t)U.out_index * nrows + row) * (size_t)V.nwave;
+        dst[mw0 + lane] += mine;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+int launch_anomaly_bits(cudaStream_t st, const StaticView &V, long long gbeg, long long gend,
+                        const UnitParams &U, unsigned *bits, int *err) {
+    if (gend <= gbeg) return 0;
+    const unsigned blocks = (unsigned)((gend - gbeg + 255) / 256);
+    anomaly_bits_kernel<<<blocks, 256, 0, st>>>(V, gbeg, gend, U, bits, err);
+    PB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_densify(cudaStream_t st, const StaticView &V, long long gbeg, long long gend,
+                   const double *ksum_tp, const unsigned long long *kmax_entry, double ethresh,
+                   double *kd) {
+    if (gend <= gbeg) return 0;
+    const unsigned blocks = (unsigned)((gend - gbeg + 255) / 256);
+    densify_kernel<<<blocks, 256, 0, st>>>(V, gbeg, gend, ksum_tp, kmax_entry, ethresh, kd);
+    PB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_segment_bounds(cudaStream_t st, const StaticView &V, long long gbeg, long long gend,
+                          double adop, int *bounds) {
+    segment_bounds_kernel<<<1, 256, sizeof(double) * V.ndop, st>>>(V, gbeg, gend, adop, bounds);
+    PB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_accumulate_dense(cudaStream_t st, const StaticView &V, int nunits,
+                            const UnitParams *units, const IsoUnit *iso_units, int iso, int row,
+                            int nrows, const double *kd, const int *bounds, const unsigned *abits,
+                            long long abits_words, double cutoff, double *out, int *err) {
+    if (nunits == 0 || V.nwave == 0) return 0;
+    const size_t smem = dense_smem_bytes();
+    PB_CUDA(cudaFuncSetAttribute(accumulate_dense_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = (V.nwave + kDenseTile - 1) / kDenseTile;
+    for (int u0 = 0; u0 < nunits; u0 += 65535) {
+        const int nu = nunits - u0 < 65535 ? nunits - u0 : 65535;
+        dim3 grid((unsigned)ntiles, (unsigned)nu);
+        accumulate_dense_kernel<<<grid, kDenseWarps * 32, smem, st>>>(
+            V, units + u0, iso_units + (size_t)u0 * V.niso, iso, row, nrows, kd, bounds, abits,
+            abits_words, cutoff, out, err);
+        PB_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace pb200

@@ -112,6 +112,7 @@ struct UnitParams {
     int dnwn;          // dynamic samples                 (:195)
     int mcount;        // resampled outputs written       (utils.h:130)
     int out_index;     // position of this unit in the caller's batch
+    int aslot;         // dense path: slot of this ofactor's anomaly bitmask (dense_kernels.cu)
     FastDiv fd_ofactor, fd_scale;
 };
 

@@ -241,6 +241,10 @@ class Engine:
     def launch_count(self):
         return int(self._lib.pb200_engine_launch_count(self._h))
 
+    def dense_units(self):
+        """(unit, isotope) pairs of the last batch evaluated by the dense-convolution kernel."""
+        return int(self._lib.pb200_engine_dense_units(self._h))
+
     def stream_ptr(self):
         """Address of the engine's cudaStream_t (for torch.cuda.ExternalStream)."""
         return int(self._lib.pb200_engine_stream(self._h) or 0)
