@@ -153,6 +153,9 @@ int64_t pb200_engine_launch_count(const pb200_engine *e);
  * csrc/dense_kernels.cu).  0: every isotope went through the gather kernels.  Same results
  * either way (_extcoeff.c:229-309); diagnostic only. */
 int64_t pb200_engine_dense_units(const pb200_engine *e);
+/* Device time (ms) the dense-convolution kernels of the last batch took (part of the
+ * accumulate time of pb200_engine_last_timing). */
+double pb200_engine_dense_ms(const pb200_engine *e);
 /* The engine's CUDA stream (cudaStream_t), so a caller can record its own events on it. */
 void *pb200_engine_stream(const pb200_engine *e);
 
@@ -189,6 +192,39 @@ int pb200_interp_ec_dev(int device, double *ext_dev, const double *etable_dev,
                         const double *ttable, const double *temperature,
                         const double *density, int nspec, int ntemp, int nlayers,
                         int nwave, int lay1, int lay2, int per_mol, void *cuda_stream);
+
+/* Device-resident table consumer ------------------------------------
+ * A handle over a table [nspec, ntemp, nlayers, nwave] that already lives in HBM (borrowed
+ * pointer: the caller keeps it alive), e.g. the rows pb200_extinction_batch_dev left there.
+ * pb200_table_interp is interp_ec / interp_ec_per_mol (src_c/_extcoeff.c:367-472; call sites
+ * pyratbay/opacity/line_sampling.py:366-391,440-463) without per-call allocation, lock or
+ * stream synchronisation: the per-layer scalars travel through a ring of pinned staging slots
+ * and the call returns once the kernel is queued on `cuda_stream` (sync != 0: waits).
+ *   overwrite != 0: ext_dev is treated as zero on entry (the reference's callers pass a
+ *                   zeroed array), so a persistent output buffer needs no memset;
+ *   overwrite == 0: accumulate (+=) like the reference's C function. */
+typedef struct pb200_table pb200_table;
+int pb200_table_create(int device, const double *etable_dev, const double *ttable, int nspec,
+                       int ntemp, int nlayers, int nwave, pb200_table **out);
+void pb200_table_destroy(pb200_table *t);
+int pb200_table_interp(pb200_table *t, const double *temperature, const double *density,
+                       int lay1, int lay2, int per_mol, double *ext_dev, int overwrite,
+                       void *cuda_stream, int sync);
+int64_t pb200_table_launch_count(const pb200_table *t);
+
+/* p/T re-gridding of a table on the device: pyratbay/tools/tools.py:1026-1107
+ * (interpolate_opacity; call site opacity/line_sampling.py:243-250).  out[t, p, w] =
+ * exp(lerp over T of lerp over log p of log table), the log of non-positive entries floored at
+ * -230, or a plain copy when take_log == 0 (same grids).  The caller supplies the brackets:
+ * output temperature i mixes table rows t_lo[i], t_hi[i] with weight t_f[i] on the upper one
+ * (same for pressure; lo == hi with weight 0 for values outside the table or an axis that is
+ * not resampled); wave_idx[nwave_out] selects the wavenumber samples (NULL: the first nwave_out).
+ * accumulate != 0 adds to out (several files of one species).  Synchronises `cuda_stream`. */
+int pb200_regrid_table_dev(int device, const double *table_dev, int ntemp, int nlayers, int nwave,
+                           const int *t_lo, const int *t_hi, const double *t_f, int ntemp_out,
+                           const int *p_lo, const int *p_hi, const double *p_f, int nlayers_out,
+                           const int *wave_idx, int nwave_out, int take_log, double *out_dev,
+                           int accumulate, void *cuda_stream);
 
 /* Optical depth (next-tier row: the step after the extinction in Pyrat.run) ------------------
  * Replaces lib._trapezoid.plane_parallel_optical_depth (src_c/_trapezoid.c:147-211) and the

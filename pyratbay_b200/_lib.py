@@ -22,11 +22,13 @@ EXPORTS = [
     "pb200_engine_get_profile", "pb200_engine_set_species", "pb200_engine_set_partition",
     "pb200_engine_set_lines", "pb200_engine_line_stats", "pb200_extinction_batch_host",
     "pb200_extinction_batch_dev", "pb200_engine_last_timing", "pb200_engine_launch_count",
-    "pb200_engine_dense_units",
+    "pb200_engine_dense_units", "pb200_engine_dense_ms",
     "pb200_interp_ec", "pb200_interp_ec_per_mol", "pb200_interp_ec_dev",
     "pb200_engine_stream", "pb200_bench_fp64", "pb200_bench_l2",
     "pb200_nearest_thresholds", "pb200_selftest_exact",
     "pb200_optical_depth", "pb200_optical_depth_dev",
+    "pb200_table_create", "pb200_table_destroy", "pb200_table_interp",
+    "pb200_table_launch_count", "pb200_regrid_table_dev",
 ]
 
 
@@ -56,8 +58,14 @@ def load():
     lib.pb200_engine_launch_count.argtypes = [c_void_p]
     lib.pb200_engine_dense_units.restype = ctypes.c_int64
     lib.pb200_engine_dense_units.argtypes = [c_void_p]
+    lib.pb200_engine_dense_ms.restype = ctypes.c_double
+    lib.pb200_engine_dense_ms.argtypes = [c_void_p]
     lib.pb200_engine_stream.restype = c_void_p
     lib.pb200_engine_stream.argtypes = [c_void_p]
+    lib.pb200_table_destroy.restype = None
+    lib.pb200_table_destroy.argtypes = [c_void_p]
+    lib.pb200_table_launch_count.restype = ctypes.c_int64
+    lib.pb200_table_launch_count.argtypes = [c_void_p]
     lib.pb200_engine_destroy.restype = None
     lib.pb200_engine_destroy.argtypes = [c_void_p]
     _lib = lib

@@ -9,7 +9,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libpb200_lbl.so"
 SOURCES = ["engine.cu", "lbl_kernels.cu", "voigt.cu", "microbench.cu",
-           "optical_depth.cu", "preprocess.cu", "dense_kernels.cu"]
+           "optical_depth.cu", "preprocess.cu", "dense_kernels.cu", "table_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -48,6 +48,18 @@ constexpr int kKRows = kDenseTile + kDenseSpanMax + 2 * J;   // K tile rows (cel
 constexpr int kWRows = kDenseSpanMax + 3 * J;                // W tile rows (output offsets)
 }  // namespace
 
+// 8-byte asynchronous global->shared copy; `on == false` writes zeros without reading.
+__device__ __forceinline__ void async_copy8(double *dst, const double *src, bool on) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst);
+    const int bytes = on ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(saddr), "l"(src), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void async_copy_wait() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 size_t dense_smem_bytes() {
     return sizeof(double) * 32 * (kKRows + kWRows) + sizeof(unsigned) * kKRows +
            sizeof(short4) * kDenseMaxStride;
@@ -141,7 +153,9 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
     const int c_ref = U.mcount >> 1;   // reference cell for the windows, far from both grid ends
 
     for (int seg = 0; seg < V.ndop; seg++) {
-        const long long sa = bounds[seg], sb = bounds[seg + 1];   // cells of Doppler sample `seg`
+        // cells of Doppler sample `seg` that this path owns (below dense_from: gather kernels)
+        const long long sa = max((long long)bounds[seg], (long long)I.dense_from);
+        const long long sb = bounds[seg + 1];
         if (sb <= sa || sb <= flo || sa >= fhi) continue;         // CTA-uniform
         const ProfileSlot ps = load_slot(V.pslot + I.ilor * V.ndop + seg);
         const int half = ps.half;
@@ -200,32 +214,35 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
             const short4 win = active ? s_win[r] : make_short4(0, 0, 0, 0);
             __syncthreads();   // the previous block's tiles are fully consumed
 
-            // (2) W tile: the unit's profile on the sub-cell offsets of this block, zero outside
-            //     each offset's window.  Reference layout: consecutive r are consecutive samples.
+            // (2)+(3) stage the tiles with asynchronous 8-byte copies (LDGSTS): every row of the
+            // warp is in flight at once, a masked element is zero-filled (source size 0).
+            //   W: the unit's profile on the sub-cell offsets of this block, zero outside each
+            //      offset's window (reference layout: consecutive r are consecutive samples);
+            //   K: the dense strengths, masked to the Doppler segment.
             for (int t = warp; t < wrows; t += kDenseWarps) {
                 const int d = w_lo + t;
-                double v = 0.0;
-                if (active && d >= win.x && d < win.y)
-                    v = dmul(prof[(long long)half - r + (long long)S * d], I.dens);
-                Ws[t][lane] = v;
+                const bool on = active && d >= win.x && d < win.y;
+                const double *src = on ? prof + ((long long)half - r + (long long)S * d) : prof;
+                async_copy8(&Ws[t][lane], src, on);
             }
-            // (3) K tile, masked to the Doppler segment, and the anomaly bits of its rows
             for (int t = warp; t < krows; t += kDenseWarps) {
                 const int c = c_lo + t;
-                const long long cell0 = (long long)c * S + rb * 32;
-                const long long cell = cell0 + lane;
-                double v = 0.0;
-                if (active && c >= 0 && cell >= sa && cell < sb) v = kd[cell];
-                Ks[t][lane] = v;
-                if (lane == 0) {
-                    unsigned bits = 0u;
-                    if (c >= 0 && cell0 < V.onwn) {
-                        const long long wi = cell0 >> 5;
-                        bits = __funnelshift_r(ab[wi], ab[wi + 1], (unsigned)(cell0 & 31));
-                    }
-                    As[t] = bits;
-                }
+                const long long cell = (long long)c * S + r;
+                const bool on = active && c >= 0 && cell >= sa && cell < sb;
+                async_copy8(&Ks[t][lane], on ? kd + cell : kd, on);
             }
+            // anomaly bits of the K rows: lane i of a warp takes the warp's i-th row
+            for (int t = warp + kDenseWarps * lane; t < krows; t += kDenseWarps * 32) {
+                const int c = c_lo + t;
+                const long long cell0 = (long long)c * S + rb * 32;
+                unsigned bits = 0u;
+                if (c >= 0 && cell0 < V.onwn) {
+                    const long long wi = cell0 >> 5;
+                    bits = __funnelshift_r(ab[wi], ab[wi + 1], (unsigned)(cell0 & 31));
+                }
+                As[t] = bits;
+            }
+            async_copy_wait();
             __syncthreads();
 
             // (4) the convolution.  At cell c_start + n output x of the warp needs offset
@@ -265,7 +282,7 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
                         if (in_n == in_a) continue;
                         const long long pi = (long long)half - r + (long long)S * d;
                         if (pi < 0 || pi > 2LL * half) continue;
-                        double pv = dmul(prof[pi], I.dens);
+                        double pv = prof[pi];
                         if (in_n) pv = -pv;
                         const int t0 = warp * J + (dmax - 1) - d;   // K row of output 0's cell
 #pragma unroll
@@ -287,6 +304,7 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == x) mine = v;
     }
+    mine = dmul(mine, I.dens);   // :271-272 (1 unless add): applied to the sum, not per line
     if (lane < J && mw0 + lane < m_end) {
         double *dst = out + ((size_t)U.out_index * nrows + row) * (size_t)V.nwave;
         dst[mw0 + lane] += mine;

@@ -165,6 +165,7 @@ struct pb200_engine {
     DevBuf<int> d_trow;
     DevBuf<ProfileSlot> d_pslot, d_tslot;
     DevBuf<double> d_dop_thr;
+    std::vector<double> dop_thr_h;
     bool has_dop_thr = false;
 
     // species
@@ -201,6 +202,8 @@ struct pb200_engine {
     std::map<int, DenseIso> dense_iso;
     bool dense_off = false;                      // set when a line list violates the path's premise
     int64_t dense_unit_isos = 0;                 // (unit, isotope) pairs of the last batch on it
+    double dense_ms = 0.0;                       // device time of the dense kernels, last batch
+    cudaEvent_t ev_dense[2] = {};
 
     // per-batch scratch (grown on demand)
     DevBuf<double> d_ksum, d_out, d_partial;
@@ -322,6 +325,7 @@ int pb200_engine_create(int device, pb200_engine **out) {
     for (int i = 0; i < 6 && err == cudaSuccess; i++) err = cudaEventCreate(&e->ev[i]);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_half, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && err == cudaSuccess; i++) err = cudaEventCreate(&e->ev_dense[i]);
     if (err != cudaSuccess) {
         delete e;
         return cuda_fail(err, "engine create", __FILE__, __LINE__);
@@ -342,6 +346,8 @@ void pb200_engine_destroy(pb200_engine *e) {
     }
     for (int i = 0; i < 6; i++)
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (int i = 0; i < 2; i++)
+        if (e->ev_dense[i]) cudaEventDestroy(e->ev_dense[i]);
     delete e;
 }
 
@@ -429,6 +435,7 @@ static int adopt_voigt_tables(pb200_engine *e, int nlor, int ndop, const double 
     for (size_t i = 0; i < pslot.size(); i++) pslot[i] = ProfileSlot{e->pindex[i], e->psize[i], 0};
     if (!rc) rc = e->d_pslot.upload(pslot.data(), pslot.size(), e->stream);
     const std::vector<double> thr = nearest_thresholds(doppler, ndop);
+    e->dop_thr_h = thr;
     e->has_dop_thr = !thr.empty();
     if (!rc && e->has_dop_thr) rc = e->d_dop_thr.upload(thr.data(), thr.size(), e->stream);
     if (rc) return rc;
@@ -922,6 +929,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
             if (cutoff > 0.0) reach = std::min<long long>(reach, (long long)(cutoff / ownstep) + 1);
             reach += 2LL * ofactor + 2;
             I.reach = (int)std::min<long long>(reach, 0x7fffffffLL);
+            I.dense_from = 0x7fffffff;
         }
         // distinct (T, Z) -> strengths pass
         std::vector<double> key(1 + niso);
@@ -990,6 +998,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
     std::vector<int> dense_isos;
     std::vector<char> unit_dense(n_units, 0);
     e->dense_unit_isos = 0;
+    e->dense_ms = 0.0;
     {
         const char *env = std::getenv("PB200_DENSE");
         const bool allow = !(env && std::strcmp(env, "0") == 0) && !e->dense_off;
@@ -1004,9 +1013,17 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
                     dense_isos.push_back(i);
         }
         if (!dense_isos.empty()) {
+            // A footprint narrower than ~24 outputs leaves the dense kernel's register tile
+            // mostly idle (a warp walks 16 + span - 1 cells whatever the span), and footprints
+            // grow with wavenumber (Doppler width): per unit and isotope the cells below
+            // `dense_from` (narrow Doppler samples) stay with the gather kernels.
+            int min_span = 24;
+            if (const char *ms = std::getenv("PB200_DENSE_MIN_SPAN")) min_span = std::atoi(ms);
+            const int cut_fine = cutoff > 0.0 ? (int)std::min(cutoff / ownstep + 1.0, 2.0e9)
+                                              : 0x7fffffff;
             bool any = false;
             for (int u = 0; u < n_units; u++) {
-                bool ok = unit_mode[u] == kModeTransposed;
+                bool ok = unit_mode[u] == kModeTransposed && e->has_dop_thr;
                 if (cutoff > 0.0) {
                     const double cs = units[u].cut_steps, f = cs - std::floor(cs);
                     if (f != 0.0 && std::min(f, 1.0 - f) < 1e-6) ok = false;
@@ -1016,8 +1033,28 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
                     if (2 * r + 2 > kDenseSpanMax || units[u].mcount < 8 * r + 2 * kDenseTile)
                         ok = false;
                 }
-                unit_dense[u] = ok;
-                any = any || ok;
+                bool some = false;
+                for (int di : dense_isos) {
+                    if (!ok) break;
+                    IsoUnit &I = iso_units[(size_t)u * niso + di];
+                    for (int j = 0; j < ndop; j++) {
+                        const long long half =
+                            std::min<long long>(e->psize[(size_t)I.ilor * ndop + j], cut_fine);
+                        if (2 * half / stride + 1 < min_span) continue;
+                        // first cell whose line can select Doppler sample j (approximate: any
+                        // split point is correct, both kernels test the same number)
+                        double cell = j == 0 ? 0.0
+                                             : (e->dop_thr_h[j] / I.adop - own0) / ownstep - 1.0;
+                        if (!(cell > 0.0)) cell = 0.0;
+                        if (cell < (double)onwn) {
+                            I.dense_from = (int)cell;
+                            some = true;
+                        }
+                        break;
+                    }
+                }
+                unit_dense[u] = ok && some;
+                any = any || unit_dense[u];
             }
             if (!any) dense_isos.clear();
         }
@@ -1101,8 +1138,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
     // staging block layout (every section 16-byte aligned)
     auto align16 = [](size_t n) { return (n + 15) & ~(size_t)15; };
     const size_t off_row = 0;
-    const size_t off_row2 = off_row + align16(sizeof(int) * niso);  // dense isotopes masked out
-    const size_t off_invt = off_row2 + align16(sizeof(int) * niso);
+    const size_t off_invt = off_row + align16(sizeof(int) * niso);
     const size_t off_invz = off_invt + align16(sizeof(double2) * tp_chunk);
     const size_t off_units = off_invz + align16(sizeof(double2) * (size_t)tp_chunk * niso);
     const size_t off_iso = off_units + align16(sizeof(UnitParams) * (size_t)n_units);
@@ -1180,8 +1216,6 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
     }
     float ms_strengths = 0.f, ms_accum = 0.f;
     size_t copied_rows = 0, split_after = 0;  // rows already sent to the host by the copy stream
-    std::vector<int> iso_row_gather(iso_row);
-    for (int di : dense_isos) iso_row_gather[di] = -1;
     // order units by strengths pass
     std::vector<int> order(n_units);
     for (int u = 0; u < n_units; u++) order[u] = u;
@@ -1209,7 +1243,6 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
             }
         }
         std::memcpy(e->h_stage + off_row, iso_row.data(), sizeof(int) * niso);
-        std::memcpy(e->h_stage + off_row2, iso_row_gather.data(), sizeof(int) * niso);
         std::memcpy(e->h_stage + off_invt, tp_t.data() + tp0, sizeof(double2) * ntc);
         std::memcpy(e->h_stage + off_invz, tp_z.data() + (size_t)tp0 * niso,
                     sizeof(double2) * ntc * niso);
@@ -1217,7 +1250,6 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         std::memcpy(e->h_stage + off_iso, ci.data(), sizeof(IsoUnit) * ci.size());
         PB_CUDA(cudaMemcpyAsync(e->d_stage.p, e->h_stage, stage_bytes, cudaMemcpyHostToDevice, st));
         const int *p_iso_row = reinterpret_cast<const int *>(e->d_stage.p + off_row);
-        const int *p_iso_row_gather = reinterpret_cast<const int *>(e->d_stage.p + off_row2);
         const double2 *p_inv_t = reinterpret_cast<const double2 *>(e->d_stage.p + off_invt);
         const double2 *p_inv_z = reinterpret_cast<const double2 *>(e->d_stage.p + off_invz);
         const UnitParams *p_units = reinterpret_cast<const UnitParams *>(e->d_stage.p + off_units);
@@ -1251,7 +1283,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
             }
             const int nu = (int)(u1 - u0);
             rc = launch_accumulate(st, V, nu, p_units + u0, p_iso_units + u0 * niso,
-                                   (cmode[u0] & 16) ? p_iso_row_gather : p_iso_row, e->d_ksum.p,
+                                   p_iso_row, e->d_ksum.p,
                                    e->d_kmax.p, nrows, ethresh, cutoff, cmode[u0] & 15, d_out,
                                    ksplit, e->d_partial.p, chunked);
             if (rc) return rc;
@@ -1275,6 +1307,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         }
         // Dense path: per strengths pass and dense isotope, scatter the group strengths onto the
         // fine grid, find the Doppler segments, and convolve for all units of the pass at once.
+        if (!dense_isos.empty()) PB_CUDA(cudaEventRecord(e->ev_dense[0], st));
         for (size_t a = 0; a < cu.size() && !dense_isos.empty();) {
             if (!(cmode[a] & 16)) {
                 a++;
@@ -1305,6 +1338,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
             }
             a = b;
         }
+        if (!dense_isos.empty()) PB_CUDA(cudaEventRecord(e->ev_dense[1], st));
         PB_CUDA(cudaEventRecord(e->ev[3], st));
         // the host vectors cu/ci must stay alive until their copies have completed
         PB_CUDA(cudaStreamSynchronize(st));
@@ -1313,6 +1347,11 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         cudaEventElapsedTime(&b, e->ev[2], e->ev[3]);
         ms_strengths += a;
         ms_accum += b;
+        if (!dense_isos.empty()) {
+            float d = 0.f;
+            cudaEventElapsedTime(&d, e->ev_dense[0], e->ev_dense[1]);
+            e->dense_ms += d;
+        }
     }
     PB_CUDA(cudaEventRecord(e->ev[3], st));
     if (out_host) {
@@ -1393,6 +1432,8 @@ int pb200_engine_last_timing(const pb200_engine *e, double ms[5]) {
 int64_t pb200_engine_launch_count(const pb200_engine *e) { return e ? e->launches : 0; }
 
 int64_t pb200_engine_dense_units(const pb200_engine *e) { return e ? e->dense_unit_isos : 0; }
+
+double pb200_engine_dense_ms(const pb200_engine *e) { return e ? e->dense_ms : 0.0; }
 
 void *pb200_engine_stream(const pb200_engine *e) { return e ? (void *)e->stream : nullptr; }
 

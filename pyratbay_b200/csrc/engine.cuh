@@ -121,6 +121,10 @@ struct IsoUnit {
     double dens;  // number density of the isotope's species if add else 1 (:271-272)
     int ilor;     // nearest Lorentz grid index          (:183)
     int reach;    // fine samples a line of this isotope can reach from its centre
+    // Split between the two accumulate paths: groups of this isotope on fine cells below
+    // `dense_from` go through the gather kernels, the others through the dense convolution
+    // (INT_MAX: all gathered, the default; dense_kernels.cu).
+    int dense_from;
 };
 
 }  // namespace pb200

@@ -270,7 +270,7 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
                 }
                 Prep p;
                 p.k = 0.0; p.base = 0; p.lo = 0; p.hi = 0;
-                if (g < ghi)
+                if (g < ghi && cur_iown < I.dense_from)
                     prepare_group<MODE>(V, U, I, s_doppler, kthr, cutoff, cur_w, cur_iown, cur_k,
                                         &p);
                 // clip to the coordinates this warp owns so that empty slots cost nothing more
@@ -549,6 +549,8 @@ __device__ __forceinline__ bool candidate_range(const StaticView &V, const UnitP
     if (fhi < 0 || flo > V.onwn - 1) return false;
     if (flo < 0) flo = 0;
     if (fhi > V.onwn - 1) fhi = V.onwn - 1;
+    if (flo >= I.dense_from) return false;   // those cells belong to the dense kernel
+    if (fhi >= I.dense_from) fhi = I.dense_from - 1;
     const int *gb = V.gbin + (size_t)iso * (V.nbins + 1);
     *glo = gb[V.fd_binw.div((int)flo)];
     *ghi = gb[V.fd_binw.div((int)fhi) + 1];
@@ -646,7 +648,7 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                 Prep p;
                 p.k = 0.0; p.base = 0; p.lo = 0; p.hi = 0;
                 bool valid = false;
-                if (g < gend)
+                if (g < gend && cur_iown < I.dense_from)   // cells >= dense_from: dense kernel
                     valid = prepare_group<kTransposed>(V, U, I, s_doppler, kthr, cutoff, cur_w,
                                                        cur_iown, cur_k, &p);
                 const int lo = max(p.lo, m0), hi = min(p.hi, tile_hi);
@@ -857,7 +859,8 @@ __global__ void __launch_bounds__(256)
 interp_ec_kernel(double *__restrict__ ext, const double *__restrict__ table,
                  const int *__restrict__ tlo, const double *__restrict__ w_lo,
                  const double *__restrict__ w_hi, const double *__restrict__ density,
-                 int nspec, int ntemp, int nlayers, int nwave, int lay1, int per_mol) {
+                 int nspec, int ntemp, int nlayers, int nwave, int lay1, int per_mol,
+                 int overwrite) {
     // VEC = 2: two adjacent samples per thread through 16-byte loads (nwave even, so every row
     // of the table and of ext is 16-byte aligned); VEC = 1: generic.
     const int k = lay1 + blockIdx.y;
@@ -869,7 +872,9 @@ interp_ec_kernel(double *__restrict__ ext, const double *__restrict__ table,
         double acc[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; v++) acc[v] = 0.0;
-        if (!per_mol) {
+        // overwrite: the destination counts as zero (what the reference's caller passes in),
+        // so no separate memset of a persistent output buffer is needed
+        if (!per_mol && !overwrite) {
             if (VEC == 2) {
                 const double2 a = *reinterpret_cast<const double2 *>(ext + (size_t)k * nwave + i);
                 acc[0] = a.x;
@@ -896,7 +901,7 @@ interp_ec_kernel(double *__restrict__ ext, const double *__restrict__ table,
 #pragma unroll
             for (int v = 0; v < VEC; v++) {
                 const double val = dadd(dmul(a[v], e1), dmul(b[v], e2));
-                if (per_mol) dst[v] = dadd(dst[v], val);
+                if (per_mol) dst[v] = dadd(overwrite ? 0.0 : dst[v], val);
                 else acc[v] = dadd(acc[v], val);
             }
         }
@@ -1011,7 +1016,8 @@ int launch_counters(cudaStream_t st, const StaticView &V, int nunits, const Unit
 
 int launch_interp_ec(cudaStream_t st, double *ext, const double *table, const int *tlo,
                      const double *w_lo, const double *w_hi, const double *density, int nspec,
-                     int ntemp, int nlayers, int nwave, int lay1, int lay2, int per_mol) {
+                     int ntemp, int nlayers, int nwave, int lay1, int lay2, int per_mol,
+                     int overwrite) {
     if (lay2 <= lay1 || nwave == 0) return 0;
     const bool vec2 = (nwave % 2 == 0) && ((uintptr_t)ext % 16 == 0) && ((uintptr_t)table % 16 == 0);
     const int per_thread = vec2 ? 2 : 1;
@@ -1021,10 +1027,10 @@ int launch_interp_ec(cudaStream_t st, double *ext, const double *table, const in
     dim3 grid((unsigned)bx, (unsigned)(lay2 - lay1));
     if (vec2)
         interp_ec_kernel<2><<<grid, 256, 0, st>>>(ext, table, tlo, w_lo, w_hi, density, nspec,
-                                                  ntemp, nlayers, nwave, lay1, per_mol);
+                                                  ntemp, nlayers, nwave, lay1, per_mol, overwrite);
     else
         interp_ec_kernel<1><<<grid, 256, 0, st>>>(ext, table, tlo, w_lo, w_hi, density, nspec,
-                                                  ntemp, nlayers, nwave, lay1, per_mol);
+                                                  ntemp, nlayers, nwave, lay1, per_mol, overwrite);
     PB_CUDA(cudaGetLastError());
     return 0;
 }

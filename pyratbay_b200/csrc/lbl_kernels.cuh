@@ -36,6 +36,7 @@ int launch_counters(cudaStream_t st, const StaticView &V, int nunits, const Unit
 
 int launch_interp_ec(cudaStream_t st, double *ext, const double *table, const int *tlo,
                      const double *w_lo, const double *w_hi, const double *density, int nspec,
-                     int ntemp, int nlayers, int nwave, int lay1, int lay2, int per_mol);
+                     int ntemp, int nlayers, int nwave, int lay1, int lay2, int per_mol,
+                     int overwrite = 0);
 
 }  // namespace pb200

@@ -245,6 +245,10 @@ class Engine:
         """(unit, isotope) pairs of the last batch evaluated by the dense-convolution kernel."""
         return int(self._lib.pb200_engine_dense_units(self._h))
 
+    def dense_ms(self):
+        """Device time (ms) of the dense-convolution kernels in the last batch."""
+        return float(self._lib.pb200_engine_dense_ms(self._h))
+
     def stream_ptr(self):
         """Address of the engine's cudaStream_t (for torch.cuda.ExternalStream)."""
         return int(self._lib.pb200_engine_stream(self._h) or 0)

@@ -45,21 +45,24 @@ def _peak_err(got, want):
 
 CASES = [
     # S = 360 (11.25 lane blocks), cutoff-limited windows, ofactor 1 .. 360 over the pressures
-    dict(nlines=100_000, wnlow=9000.0, wnhigh=9400.0, wnstep=0.25, wnosamp=360, cutoff=10.0,
+    dict(nlines=100_000, wnlow=9000.0, wnhigh=9400.0, wnstep=0.25, wnosamp=360, cutoff=10.07,
          extent=60.0, nlayers=11),
     # many skipped lines
-    dict(nlines=100_000, wnlow=9000.0, wnhigh=9400.0, wnstep=0.25, wnosamp=360, cutoff=10.0,
+    dict(nlines=100_000, wnlow=9000.0, wnhigh=9400.0, wnstep=0.25, wnosamp=360, cutoff=10.07,
          extent=60.0, nlayers=7, ethresh=1e-6),
     # no fixed cutoff: windows set by the profile sizes
     dict(nlines=60_000, wnlow=9000.0, wnhigh=9400.0, wnstep=0.25, wnosamp=240, cutoff=0.0,
          extent=8.0, nlayers=9),
     # heavy co-adding (4 lines per fine cell), S = 120
-    dict(nlines=800_000, wnlow=9000.0, wnhigh=9400.0, wnstep=0.25, wnosamp=120, cutoff=12.0,
+    dict(nlines=800_000, wnlow=9000.0, wnhigh=9400.0, wnstep=0.25, wnosamp=120, cutoff=12.13,
          extent=40.0, nlayers=7),
-    # S = 840 as in the table benchmark, 1 cm-1 output step
-    dict(nlines=200_000, wnlow=8000.0, wnhigh=9600.0, wnstep=1.0, wnosamp=840, cutoff=25.0,
-         extent=80.0, nlayers=9),
+    # the table benchmark's sampling: 0.33 cm-1 output step, S = 840, cutoff 25 cm-1
+    dict(nlines=200_000, wnlow=8000.0, wnhigh=8600.0, wnstep=0.33, wnosamp=840, cutoff=25.0,
+         extent=300.0, nlayers=9),
 ]
+# (cutoff/(ownstep*ofactor) must not be within 1e-6 of an integer for the dense path: the
+# reference's (int)(idwn +- cutoff/dwnstep) is then position dependent and the engine keeps
+# such units on the gather path; test_near_integer_cutoff_steps_stay_on_the_gather_path)
 
 
 @pytest.mark.parametrize("kwargs", CASES)
@@ -68,6 +71,7 @@ def test_dense_path_matches_oracle_and_gather(kwargs, monkeypatch):
     temps, dens = case.atm.temp, case.atm.d
     isoz = helpers.partition(case, temps).T
     monkeypatch.setenv("PB200_DENSE_MIN_OCC", "0.0005")      # every isotope with lines
+    monkeypatch.setenv("PB200_DENSE_MIN_SPAN", "1")          # ... and all of their cells
     for add in (0, 1):
         args = (temps, dens, isoz, case.iso_mol_index, 1, case.ethresh, add, 0)
         want, wcnt = _oracle(case, temps, dens, isoz, add)
@@ -91,7 +95,7 @@ def test_dense_main_isotope_gather_for_the_rest(monkeypatch):
     """Threshold between the isotopes' occupancies: 75 % of the lines go dense, the minor
     isotopes through the gather kernels, both into the same output rows; per-species rows."""
     case = helpers.synthetic_case(nlines=150_000, wnlow=9000.0, wnhigh=9400.0, wnstep=0.25,
-                                  wnosamp=360, cutoff=10.0, extent=60.0, nlayers=7)
+                                  wnosamp=360, cutoff=10.07, extent=60.0, nlayers=7)
     temps, dens = case.atm.temp, case.atm.d
     isoz = helpers.partition(case, temps).T
     nfine = len(case.spec.own)
@@ -113,7 +117,7 @@ def test_dense_path_lines_on_grid_points(monkeypatch):
     """Lines exactly on fine-grid samples and exactly half way between them: the cases where
     the dynamic index of a line sits on a rounding edge (anomalous cells)."""
     base = helpers.synthetic_case(nlines=50_000, wnlow=9000.0, wnhigh=9400.0, wnstep=0.25,
-                                  wnosamp=360, cutoff=10.0, extent=60.0, nlayers=9)
+                                  wnosamp=360, cutoff=10.07, extent=60.0, nlayers=9)
     own = base.spec.own
     rng = np.random.default_rng(5)
     lwn = base.lwn.copy()
@@ -138,4 +142,21 @@ def test_dense_path_lines_on_grid_points(monkeypatch):
     eng.close()
     want, wcnt = _oracle(case, temps, dens, isoz, 0)
     assert np.array_equal(cnt[:, :4], wcnt)
+    assert _peak_err(got, want) < TOL_PEAK
+
+
+def test_near_integer_cutoff_steps_stay_on_the_gather_path(monkeypatch):
+    """cutoff/dwnstep within rounding of an integer (the reference's defaults: 25 cm-1, 1 cm-1
+    steps): (int)(idwn +- cutoff/dwnstep) depends on the magnitude of idwn, the windows are not
+    translation invariant and the engine must not take the dense path."""
+    case = helpers.synthetic_case(nlines=100_000, wnlow=9000.0, wnhigh=9400.0, wnstep=0.25,
+                                  wnosamp=360, cutoff=10.0, extent=60.0, nlayers=5)
+    temps, dens = case.atm.temp, case.atm.d
+    isoz = helpers.partition(case, temps).T
+    monkeypatch.setenv("PB200_DENSE_MIN_OCC", "0.0005")
+    eng = _engine(case)
+    got = eng.extinction_batch(temps, dens, isoz, case.iso_mol_index, 1, case.ethresh, 0, 0)
+    assert eng.dense_units() == 0
+    eng.close()
+    want, _ = _oracle(case, temps, dens, isoz, 0)
     assert _peak_err(got, want) < TOL_PEAK
