@@ -44,8 +44,8 @@ namespace pb200 {
 
 namespace {
 constexpr int J = kDenseJ;
-constexpr int kKRows = kDenseTile + kDenseSpanMax + 2 * J;   // K tile rows (cells)
-constexpr int kWRows = kDenseSpanMax + 3 * J;                // W tile rows (output offsets)
+constexpr int kKRows = kDenseTile + kDenseSpanMax;           // K tile rows (cells)
+constexpr int kWRows = kDenseSpanMax + 2 * J;                // W tile rows (output offsets)
 }  // namespace
 
 // 8-byte asynchronous global->shared copy; `on == false` writes zeros without reading.
@@ -61,7 +61,7 @@ __device__ __forceinline__ void async_copy_wait() {
 }
 
 size_t dense_smem_bytes() {
-    return sizeof(double) * 32 * (kKRows + kWRows) + sizeof(unsigned) * kKRows +
+    return sizeof(double) * kDenseLanes * (kKRows + kWRows) + sizeof(unsigned short) * kKRows +
            sizeof(short4) * kDenseMaxStride;
 }
 
@@ -119,27 +119,60 @@ segment_bounds_kernel(StaticView V, long long gbeg, long long gend, double adop,
     }
 }
 
-__global__ void __launch_bounds__(kDenseWarps * 32, 1)
+// One sub-step of the convolution: cell `krow + I` of the warp's walk.  The window registers
+// rotate statically: output x reads w[(x - I) mod J], the register freed by output J-1 takes
+// the new offset.
+template <int I>
+__device__ __forceinline__ void dense_step(const double *__restrict__ kp,
+                                           const double *__restrict__ wp, double (&w)[kDenseJ],
+                                           double (&acc)[kDenseJ]) {
+    constexpr int J = kDenseJ;
+    const double kv = kp[I * kDenseLanes];
+    w[(J - I) % J] = wp[-I * kDenseLanes];
+#pragma unroll
+    for (int x = 0; x < J; x++) acc[x] = fma(kv, w[(x - I + J) % J], acc[x]);
+}
+
+template <int I>
+__device__ __forceinline__ void dense_steps(const double *__restrict__ kp,
+                                            const double *__restrict__ wp, double (&w)[kDenseJ],
+                                            double (&acc)[kDenseJ], int count) {
+    if constexpr (I < kDenseJ) {
+        if (I < count) {   // warp-uniform
+            dense_step<I>(kp, wp, w, acc);
+            dense_steps<I + 1>(kp, wp, w, acc, count);
+        }
+    }
+}
+
+// Thread layout: a warp owns 2 x J consecutive outputs and 16 sub-cell offsets: lanes 0-15 hold
+// offsets r0..r0+15 for the first J outputs, lanes 16-31 the same offsets for the next J.  Tile
+// rows are 16 doubles (128 B); the two half-warps read two different rows per load, which is
+// the same two shared-memory wavefronts as one 256-byte row.  Half-width rows keep the tiles
+// under 100 KB, so two CTAs share an SM: one stages while the other computes.
+__global__ void __launch_bounds__(kDenseWarps * 32, 2)
 accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
                         const IsoUnit *__restrict__ iso_units, int iso, int row, int nrows,
                         const double *__restrict__ kd, const int *__restrict__ bounds,
                         const unsigned *__restrict__ abits, long long abits_words, double cutoff,
                         double *__restrict__ out, int *__restrict__ err) {
+    constexpr int L = kDenseLanes;
     extern __shared__ double s_dyn[];
-    double (*Ks)[32] = reinterpret_cast<double (*)[32]>(s_dyn);   // [kKRows]: cell c_lo + t
-    double (*Ws)[32] = Ks + kKRows;                               // [kWRows]: offset w_lo + t
-    unsigned *As = reinterpret_cast<unsigned *>(Ws + kWRows);     // [kKRows] anomaly bits of a row
+    double (*Ks)[L] = reinterpret_cast<double (*)[L]>(s_dyn);     // [kKRows]: cell c_lo + t
+    double (*Ws)[L] = Ks + kKRows;                                // [kWRows]: offset w_lo + t
+    unsigned short *As = reinterpret_cast<unsigned short *>(Ws + kWRows);   // [kKRows] anomaly bits
     short4 *s_win = reinterpret_cast<short4 *>(As + kKRows);      // [S] windows per sub-cell offset
     __shared__ int s_dmin, s_dmax;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane >> 4, l16 = lane & (L - 1);
     const UnitParams U = units[blockIdx.y];
     const IsoUnit I = iso_units[(size_t)blockIdx.y * V.niso + iso];
     const int S = V.tstride;
     const int ms = blockIdx.x * kDenseTile;
     const int m_end = min(ms + kDenseTile, min(V.nwave, U.mcount));   // exclusive
     if (ms >= m_end) return;
-    const int mw0 = ms + warp * J;
+    const int orow = (warp * 2 + grp) * J;       // first output of this half-warp within the tile
     const unsigned *__restrict__ ab = abits + (long long)U.aslot * abits_words;
 
     double acc[J];
@@ -201,71 +234,65 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
         }
 
         const int c_lo = ms - (dmax - 1);             // first cell that reaches the tile
-        const int w_lo = dmin - 2 * J;                // first offset held in Ws
-        const int nsteps = J + (dmax - dmin) - 1;     // cells that reach one warp's outputs
-        const int niter = (nsteps + J - 1) / J;
-        const int krows = kDenseTile - J + niter * J;
+        const int w_lo = dmin - J;                    // first offset held in Ws
+        const int nsteps = J + (dmax - dmin) - 1;     // cells that reach one half-warp's outputs
+        const int krows = kDenseTile - J + nsteps;
         const int wrows = dmax + J - w_lo;
-        const int nrb = (S + 31) >> 5;
+        const int nrb = (S + L - 1) / L;
 
         for (int rb = 0; rb < nrb; rb++) {
-            const int r = rb * 32 + lane;
+            const int r = rb * L + l16;
             const bool active = r < S;
             const short4 win = active ? s_win[r] : make_short4(0, 0, 0, 0);
             __syncthreads();   // the previous block's tiles are fully consumed
 
-            // (2)+(3) stage the tiles with asynchronous 8-byte copies (LDGSTS): every row of the
-            // warp is in flight at once, a masked element is zero-filled (source size 0).
+            // (2)+(3) stage the tiles with asynchronous 8-byte copies (LDGSTS): all rows of a
+            // warp are in flight at once, a masked element is zero-filled (source size 0).
             //   W: the unit's profile on the sub-cell offsets of this block, zero outside each
             //      offset's window (reference layout: consecutive r are consecutive samples);
             //   K: the dense strengths, masked to the Doppler segment.
-            for (int t = warp; t < wrows; t += kDenseWarps) {
+            for (int t = warp * 2 + grp; t < wrows; t += kDenseWarps * 2) {
                 const int d = w_lo + t;
                 const bool on = active && d >= win.x && d < win.y;
                 const double *src = on ? prof + ((long long)half - r + (long long)S * d) : prof;
-                async_copy8(&Ws[t][lane], src, on);
+                async_copy8(&Ws[t][l16], src, on);
             }
-            for (int t = warp; t < krows; t += kDenseWarps) {
+            for (int t = warp * 2 + grp; t < krows; t += kDenseWarps * 2) {
                 const int c = c_lo + t;
                 const long long cell = (long long)c * S + r;
                 const bool on = active && c >= 0 && cell >= sa && cell < sb;
-                async_copy8(&Ks[t][lane], on ? kd + cell : kd, on);
+                async_copy8(&Ks[t][l16], on ? kd + cell : kd, on);
             }
-            // anomaly bits of the K rows: lane i of a warp takes the warp's i-th row
-            for (int t = warp + kDenseWarps * lane; t < krows; t += kDenseWarps * 32) {
+            // anomaly bits of the K rows: thread i of the CTA takes rows i, i + 256, ...
+            for (int t = threadIdx.x; t < krows; t += blockDim.x) {
                 const int c = c_lo + t;
-                const long long cell0 = (long long)c * S + rb * 32;
+                const long long cell0 = (long long)c * S + rb * L;
                 unsigned bits = 0u;
                 if (c >= 0 && cell0 < V.onwn) {
                     const long long wi = cell0 >> 5;
                     bits = __funnelshift_r(ab[wi], ab[wi + 1], (unsigned)(cell0 & 31));
                 }
-                As[t] = bits;
+                As[t] = (unsigned short)(bits & 0xffffu);
             }
             async_copy_wait();
             __syncthreads();
 
-            // (4) the convolution.  At cell c_start + n output x of the warp needs offset
-            //     (dmax-1) + x - n; the window registers rotate statically: w[(x - i) mod J].
+            // (4) the convolution.  At its n-th cell, output x of the half-warp needs offset
+            //     (dmax-1) + x - n.
             {
                 double w[J];
 #pragma unroll
-                for (int x = 1; x < J; x++) w[x] = Ws[(dmax - 1 + x) - w_lo][lane];
+                for (int x = 1; x < J; x++) w[x] = Ws[(dmax - 1 + x) - w_lo][l16];
                 w[0] = 0.0;
-                int krow = warp * J;
-                int wrow = (dmax - 1) - w_lo;
-                for (int it = 0; it < niter; it++) {
-#pragma unroll
-                    for (int i = 0; i < J; i++) {
-                        const double kv = Ks[krow + i][lane];
-                        w[(J - i) % J] = Ws[wrow - i][lane];
-#pragma unroll
-                        for (int x = 0; x < J; x++)
-                            acc[x] = fma(kv, w[(x - i + J) % J], acc[x]);
-                    }
-                    krow += J;
-                    wrow -= J;
+                const double *kp = &Ks[orow][l16];
+                const double *wp = &Ws[(dmax - 1) - w_lo][l16];
+                int n = 0;
+                for (; n + J <= nsteps; n += J) {
+                    dense_steps<0>(kp, wp, w, acc, J);
+                    kp += J * L;
+                    wp -= J * L;
                 }
+                dense_steps<0>(kp, wp, w, acc, nsteps - n);
             }
 
             // (5) anomalous cells of this block: add the samples their window has and the
@@ -284,30 +311,30 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
                         if (pi < 0 || pi > 2LL * half) continue;
                         double pv = prof[pi];
                         if (in_n) pv = -pv;
-                        const int t0 = warp * J + (dmax - 1) - d;   // K row of output 0's cell
+                        const int t0 = orow + (dmax - 1) - d;   // K row of output 0's cell
 #pragma unroll
                         for (int x = 0; x < J; x++)
-                            if ((As[t0 + x] >> lane) & 1u) acc[x] = fma(Ks[t0 + x][lane], pv, acc[x]);
+                            if ((As[t0 + x] >> l16) & 1u) acc[x] = fma(Ks[t0 + x][l16], pv, acc[x]);
                     }
                 }
             }
         }
     }
 
-    // (6) sum the 32 sub-cell offsets of a warp and add to the output row (the gather kernels
-    //     have written it: other isotopes, or zeros)
+    // (6) sum the 16 sub-cell offsets of a half-warp and add to the output row (the gather
+    //     kernels have written it: other isotopes and narrow footprints, or zeros)
     double mine = 0.0;
 #pragma unroll
     for (int x = 0; x < J; x++) {
         double v = acc[x];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == x) mine = v;
+        for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (l16 == x) mine = v;
     }
     mine = dmul(mine, I.dens);   // :271-272 (1 unless add): applied to the sum, not per line
-    if (lane < J && mw0 + lane < m_end) {
+    if (ms + orow + l16 < m_end) {
         double *dst = out + ((size_t)U.out_index * nrows + row) * (size_t)V.nwave;
-        dst[mw0 + lane] += mine;
+        dst[ms + orow + l16] += mine;
     }
 }
 

@@ -5,9 +5,10 @@
 
 namespace pb200 {
 
-constexpr int kDenseJ = 16;                              // outputs per warp (register tile)
-constexpr int kDenseWarps = 16;                          // warps per CTA
-constexpr int kDenseTile = kDenseJ * kDenseWarps;        // outputs per CTA
+constexpr int kDenseJ = 16;                              // outputs per half-warp (register tile)
+constexpr int kDenseLanes = 16;                          // sub-cell offsets per half-warp / tile row
+constexpr int kDenseWarps = 8;                           // warps per CTA
+constexpr int kDenseTile = 2 * kDenseJ * kDenseWarps;    // outputs per CTA
 constexpr int kDenseSpanMax = 192;   // widest line footprint (outputs) the shared tiles hold
 constexpr int kDenseMaxStride = 1024;  // fine samples per output sample (window table size)
 

@@ -254,6 +254,93 @@ class Engine:
         return int(self._lib.pb200_engine_stream(self._h) or 0)
 
 
+class DeviceTable:
+    """Handle over a cross-section table [nspec, ntemp, nlayers, nwave] resident in HBM
+    (pb200_table_*): temperature interpolation without per-call allocation or synchronisation.
+    `table` is anything with data_ptr() (a torch CUDA tensor); it is kept alive here."""
+
+    def __init__(self, table, ttable, device=0):
+        self._lib = _lib.load()
+        _lib.require_device()
+        self.table = table
+        self.shape = tuple(int(v) for v in table.shape)
+        if len(self.shape) != 4:
+            raise ValueError("DeviceTable: table must be [nspec, ntemp, nlayers, nwave]")
+        nspec, ntemp, nlayers, nwave = self.shape
+        tt = _f64(ttable)
+        if tt.shape != (ntemp,):
+            raise ValueError("DeviceTable: ttable must have ntemp samples")
+        handle = ctypes.c_void_p()
+        check(self._lib.pb200_table_create(
+            ctypes.c_int(int(device)), ctypes.c_void_p(table.data_ptr()), _dp(tt),
+            ctypes.c_int(nspec), ctypes.c_int(ntemp), ctypes.c_int(nlayers), ctypes.c_int(nwave),
+            ctypes.byref(handle)))
+        self._h = handle
+        self._fn = self._lib.pb200_table_interp
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pb200_table_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def interp(self, temperature, density, lay1, lay2, per_mol, ext_ptr, overwrite=True,
+               stream=0, sync=False):
+        """Queue interp_ec / interp_ec_per_mol into the device buffer at `ext_ptr`
+        ([nlayers, nwave] or [nspec, nlayers, nwave]).  Returns without waiting unless sync."""
+        nspec, _, nlayers, _ = self.shape
+        te = np.ascontiguousarray(temperature, np.float64)
+        de = np.ascontiguousarray(density, np.float64)
+        if te.size != nlayers or de.size != nlayers * nspec:
+            raise ValueError("DeviceTable.interp: inconsistent temperature/density shapes")
+        status = self._fn(self._h, te.ctypes.data_as(c_double_p), de.ctypes.data_as(c_double_p),
+                          ctypes.c_int(int(lay1)), ctypes.c_int(int(lay2)),
+                          ctypes.c_int(int(per_mol)), ctypes.c_void_p(ext_ptr),
+                          ctypes.c_int(int(overwrite)), ctypes.c_void_p(stream),
+                          ctypes.c_int(int(sync)))
+        if status:
+            check(status)
+
+    def launch_count(self):
+        return int(self._lib.pb200_table_launch_count(self._h))
+
+
+def regrid_table_device(table_ptr, shape, t_brackets, p_brackets, wave_idx, out_ptr, take_log,
+                        accumulate=False, device=0, stream=0):
+    """pb200_regrid_table_dev: `shape` = (ntemp, nlayers, nwave) of the source table on the
+    device; *_brackets = (lo, hi, weight) arrays per output sample; wave_idx int32 or None."""
+    lib = _lib.load()
+    ntemp, nlayers, nwave = (int(v) for v in shape)
+    c_int_p = ctypes.POINTER(ctypes.c_int)
+
+    def ints(a):
+        a = np.ascontiguousarray(a, np.int32)
+        return a, a.ctypes.data_as(c_int_p)
+    tlo, ptlo = ints(t_brackets[0])
+    thi, pthi = ints(t_brackets[1])
+    tf = _f64(t_brackets[2])
+    plo, pplo = ints(p_brackets[0])
+    phi, pphi = ints(p_brackets[1])
+    pf = _f64(p_brackets[2])
+    if wave_idx is None:
+        widx, pw, nwave_out = None, None, nwave
+    else:
+        widx, pw = ints(wave_idx)
+        nwave_out = len(widx)
+    check(lib.pb200_regrid_table_dev(
+        ctypes.c_int(int(device)), ctypes.c_void_p(table_ptr), ctypes.c_int(ntemp),
+        ctypes.c_int(nlayers), ctypes.c_int(nwave), ptlo, pthi, _dp(tf), ctypes.c_int(len(tlo)),
+        pplo, pphi, _dp(pf), ctypes.c_int(len(plo)), pw, ctypes.c_int(nwave_out),
+        ctypes.c_int(int(take_log)), ctypes.c_void_p(out_ptr), ctypes.c_int(int(accumulate)),
+        ctypes.c_void_p(stream)))
+    return (len(tlo), len(plo), nwave_out)
+
+
 def device_ceilings(device=0, l2_mbytes=32, reps=3):
     """Measured fp64-FMA TFLOP/s and L2-resident read GB/s (bench.py roofline denominators)."""
     lib = _lib.load()

@@ -51,8 +51,10 @@ def main():
             os.environ["PB200_DENSE"] = dense
             os.environ["PB200_DENSE_MIN_SPAN"] = span
             for _ in range(2):
-                _, cnt = eng.extinction_batch(temps, dens, isoz, w.iso_mol_index, 1, 1e-30, 0, 0,
-                                              out_device_ptr=out.data_ptr(), counters=(name == "gather"))
+                res = eng.extinction_batch(temps, dens, isoz, w.iso_mol_index, 1, 1e-30, 0, 0,
+                                           out_device_ptr=out.data_ptr(),
+                                           counters=(name == "gather"))
+                cnt = res[1] if res is not None else None
             t = eng.last_timing()
             rec[name + "_acc_ms"] = round(float(t["accumulate_ms"]), 2)
             if dense == "1":

@@ -355,6 +355,101 @@ def test_line_sample_matches_reference():
         ls.calc_cross_section(np.full(ls.nlayers, 5000.0))
 
 
+def test_table_regridding_matches_reference():
+    """pb200_regrid_table_dev (tools/tools.py:1026-1107 on the device) against the outputs of the
+    unmodified reference's interpolate_opacity (tests/golden/make_golden_regrid.py): both axes
+    with out-of-range and on-node samples, one axis only, wavenumber mask + thinning, the -230
+    floor of zero / underflowing entries."""
+    from pyratbay_b200 import io
+    from pyratbay_b200.line_sampling import interpolate_opacity
+    g = helpers.golden("mock_regrid.npz")
+    path = os.path.join(helpers.GOLDEN, "mock_opacity_file.npz")
+    _, temp, press, _wn = io.read_opacity(path, extract="arrays")
+    tol = dict(rtol=1e-12, atol=0)
+    np.testing.assert_allclose(interpolate_opacity(path, g["t_both"], g["p_both"]), g["cs_both"], **tol)
+    np.testing.assert_allclose(interpolate_opacity(path, g["t_only"], press, g["mask"], 3),
+                               g["cs_t_only"], **tol)
+    np.testing.assert_allclose(interpolate_opacity(path, temp, g["p_only"]), g["cs_p_only"], **tol)
+    same = interpolate_opacity(path, temp, press)
+    assert np.array_equal(same, io.read_opacity(path, extract="opacity"))
+
+
+def test_table_regridding_floor_of_zero_entries(tmp_path):
+    from pyratbay_b200 import io
+    from pyratbay_b200.line_sampling import interpolate_opacity
+    g = helpers.golden("mock_regrid.npz")
+    path = os.path.join(helpers.GOLDEN, "mock_opacity_file.npz")
+    _, species, temp, press, wn, _ = io.read_opacity(path, extract="all")
+    zpath = str(tmp_path / "zero_table.npz")
+    io.write_opacity(zpath, species, temp, press, wn, g["zero_table"])
+    got = interpolate_opacity(zpath, g["t_both"], g["p_both"])
+    want = g["cs_zero"]
+    assert np.all(np.isfinite(got)) and got.min() >= 0
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-300)
+
+
+def test_line_sample_regridded_axes_and_str():
+    """Line_Sample built on other pressure / temperature axes than the file's (device
+    re-gridding), its extinction and its text form against the reference."""
+    import pyratbay_b200 as pb
+    g = helpers.golden("mock_regrid.npz")
+    path = os.path.join(helpers.GOLDEN, "mock_opacity_file.npz")
+    ls = pb.Line_Sample(path, pressure=g["p_both"][1:6], temperature=g["t_both"][1:6])
+    np.testing.assert_allclose(ls.cs_table, g["ls_cs_table"], rtol=1e-12)
+    dens = np.full((5, 1), 1.0e12)
+    np.testing.assert_allclose(ls.calc_extinction_coefficient(g["ls_temp"], dens), g["ls_ec"],
+                               rtol=1e-12)
+    assert str(ls).replace(path, "FILE") == str(g["ls_str"])
+
+
+def test_line_sample_from_device_table_without_file_round_trip(tmp_path):
+    """compute_opacity leaves the table in HBM; Line_Sample(tables=[pyrat.ex]) consumes it there
+    and gives the bits of a Line_Sample built from the .npz file; device_out=True queues the
+    interpolation without synchronising and is bit-exact with the oracle's interp_ec."""
+    import torch
+    import pyratbay_b200 as pb
+    from pyratbay_b200 import tli as ptli, workloads
+    from pyratbay_b200.pyrat import Pyrat
+    w = workloads.table_workload(100_000, ntemp=5, nlayers=6, nwave=1500, wl_low_um=1.0,
+                                 wl_high_um=1.2)
+    tli_path = str(tmp_path / "lines.tli")
+    wn, elow, gf, iso, counts = w.make_lines()
+    ptli.write_tli(tli_path, [w.db], [{"wn": wn, "elow": elow, "gf": gf, "iso_id": iso,
+                                       "n_lines_iso": counts}], w.inputs["wnlow"], w.inputs["wnhigh"])
+    cs = str(tmp_path / "table.npz")
+    pyrat = Pyrat(dict(w.inputs, tlifile=[tli_path], sampled_cs=[cs]), atm=w.atm, device=0)
+    pyrat.compute_opacity()
+    ex = pyrat.ex
+    from_dev = pb.Line_Sample(tables=[ex])
+    from_file = pb.Line_Sample(cs)
+    assert from_dev.cs_table_device.data_ptr() != ex.etable_dev.data_ptr()   # its own copy
+    assert np.array_equal(from_dev.cs_table, from_file.cs_table)
+    assert np.array_equal(from_dev.cs_table[0], ex.etable)
+    temp = np.linspace(350.0, 850.0, 6)
+    dens = np.geomspace(1e10, 1e18, 6)[:, None]
+    a = from_dev.calc_extinction_coefficient(temp, dens)
+    b = from_file.calc_extinction_coefficient(temp, dens)
+    assert np.array_equal(a, b)
+    orc = helpers.oracle_module()
+    want = np.zeros((6, 1500))
+    orc.interp_ec(want, from_file.cs_table, from_file.temp, temp, dens, 0, 6)
+    assert np.array_equal(a, want)
+    # asynchronous, device-resident result: same bits, many calls back to back
+    for _ in range(20):
+        d = from_dev.calc_extinction_coefficient(temp, dens, device_out=True)
+    assert isinstance(d, torch.Tensor) and d.is_cuda
+    assert np.array_equal(d.cpu().numpy(), want)
+    per = from_dev.calc_extinction_coefficient(temp, dens, per_mol=True, device_out=True)
+    wantm = np.zeros((1, 6, 1500))
+    orc.interp_ec_per_mol(wantm, from_file.cs_table, from_file.temp, temp, dens, 0, 6)
+    assert np.array_equal(per.cpu().numpy(), wantm)
+    # a layer range leaves the other rows at zero, as the reference's zeroed array
+    part = from_dev.calc_extinction_coefficient(temp, dens, layer=(2, 4))
+    wantp = np.zeros((6, 1500))
+    orc.interp_ec(wantp, from_file.cs_table, from_file.temp, temp, dens, 2, 4)
+    assert np.array_equal(part, wantp)
+
+
 # ------------------------------------------------------------- full-size configs[1] checks
 @pytest.fixture(scope="module")
 def full_size_engine():

@@ -169,22 +169,17 @@ def test_opacity_file_round_trip(tmp_path):
     assert sp == "H2O" and np.array_equal(tab, g["etable"]) and np.array_equal(w, g["wn"])
 
 
-def test_interpolate_opacity_regridding(tmp_path):
-    from pyratbay_b200.line_sampling import interpolate_opacity
-    path = os.path.join(helpers.GOLDEN, "mock_opacity_file.npz")
-    g = helpers.golden("mock_opacity_table.npz")
-    same = interpolate_opacity(path, g["temp"], g["press"])
-    assert np.array_equal(same, g["etable"])
-    temp2 = np.array([450.0, 1234.0])
-    press2 = np.array([1e-7, 3e-3, 50.0])
-    cs = interpolate_opacity(path, temp2, press2)
-    assert cs.shape == (2, 3, 100) and np.all(np.isfinite(cs)) and np.all(cs >= 0)
-    # log-linear between bracketing nodes
-    lo, hi = g["etable"][0], g["etable"][1]
-    with np.errstate(divide="ignore"):
-        want = np.exp(0.5 * (np.maximum(np.log(lo), -230) + np.maximum(np.log(hi), -230)))
-    cs_t = interpolate_opacity(path, np.array([450.0, 3000.0]), None)
-    np.testing.assert_allclose(cs_t[0], want, rtol=1e-12)
+def test_regridding_brackets():
+    """Host part of the table re-gridding (the kernel takes brackets and weights): piecewise
+    linear with edge values outside the nodes, exact rows at the nodes (interp1d 'slinear' with
+    fill_value=(first, last), tools/tools.py:1083-1105)."""
+    from pyratbay_b200.line_sampling import _brackets, _needs_resampling
+    nodes = np.array([300.0, 600.0, 900.0, 1500.0])
+    lo, hi, f = _brackets(nodes, [100.0, 300.0, 450.0, 900.0, 1499.0, 1500.0, 2000.0])
+    assert list(lo) == [0, 0, 0, 2, 2, 3, 3] and list(hi) == [0, 0, 1, 2, 3, 3, 3]
+    np.testing.assert_allclose(f, [0, 0, 0.5, 0, 599.0 / 600.0, 0, 0], rtol=1e-15)
+    assert not _needs_resampling(nodes, None) and not _needs_resampling(nodes, nodes * 1.005)
+    assert _needs_resampling(nodes, nodes[:3]) and _needs_resampling(nodes, nodes * 1.02)
 
 
 # --------------------------------------------------------------------------- C-ABI surface
