@@ -479,6 +479,8 @@ def run_table(args):
     def api_step():
         pyrat.compute_opacity(write=False, nchunks=args.nchunks)
 
+    dense_ms = []
+
     def timed(fn):
         """K table builds between two CUDA events; every build ends with the host blocked on
         the engine's stream and the scatter of the gathered rows queued on torch's current
@@ -494,6 +496,7 @@ def run_table(args):
             fn()
             acc_ms.append(ex.timing["accumulate_ms"])
             str_ms.append(ex.timing["strengths_ms"])
+            dense_ms.append(ex.timing["dense_ms"])
         e1.record()
         barrier()
         mine = e0.elapsed_time(e1)
@@ -510,6 +513,7 @@ def run_table(args):
     e2e_ms, _, _, _, _ = timed(api_step)
     clocks = sampler.stop() if rank == 0 else None
 
+    ex_timing_units = ex.timing["dense_units"]
     table = ex.etable_dev
     finite = bool(torch.isfinite(table).all().item()) and bool((table >= 0).all().item())
     checksum = float(table.sum(dtype=torch.float64).item())
@@ -605,6 +609,8 @@ def run_table(args):
                    "dynamic_samples_rank0": int(cnt[:, 3].sum()),
                    "gathered_samples_rank0": int(cnt[:, 4].sum()),
                    "strengths_ms_rank0": str_ms, "accumulate_ms_rank0": acc_ms,
+                   "dense_kernels_ms_rank0": float(np.mean(dense_ms[:args.steps])),
+                   "dense_unit_isotopes_rank0": int(ex_timing_units),
                    "accumulate_ms_per_rank": per_rank_acc, "step_ms_per_rank": per_rank_step,
                    "allgather_chunks": launches_per_step if world > 1 else 0,
                    "setup_s": setup_s, "tli_write_s": tli_write_s,

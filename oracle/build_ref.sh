@@ -21,4 +21,19 @@ for m in _extcoeff vprofile; do
     gcc -shared -fPIC -O3 -ffast-math -w -I"$PYINC" -I"$NPINC" -I"$REF/src_c/include" \
         "$REF/src_c/$m.c" -o "$OUT/$m$EXT" -lm
 done
+# A scratch copy of the reference's PYTHON package with its own C modules, except the two the
+# engine replaces (tests/test_gpu_dropin.py runs the unmodified reference on the GPU engine
+# through pyratbay_b200/shim).  Git-ignored like the rest of oracle/_ref.
+PKG="$OUT/shimmed/pyratbay"
+rm -rf "$OUT/shimmed"
+mkdir -p "$OUT/shimmed"
+cp -r "$REF/pyratbay" "$PKG"
+mkdir -p "$PKG/lib"
+for f in "$REF"/src_c/*.c; do
+    m=$(basename "$f" .c)
+    case "$m" in _extcoeff|vprofile) continue;; esac
+    gcc -shared -fPIC -O3 -ffast-math -w -I"$PYINC" -I"$NPINC" -I"$REF/src_c/include" \
+        "$f" -o "$PKG/lib/$m$EXT" -lm
+done
+PYTHONPATH="$HERE/.." $PY -c "from pyratbay_b200.shim import install_into; install_into('$PKG/lib')"
 echo "built: $(ls "$OUT")"

@@ -56,6 +56,25 @@ __device__ __forceinline__ void async_copy8(double *dst, const double *src, bool
                  : "memory");
 }
 
+__device__ __forceinline__ void async_copy8s(unsigned saddr, const double *src, bool on) {
+    const int bytes = on ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(saddr), "l"(src), "r"(bytes)
+                 : "memory");
+}
+
+// 16-byte form (source and destination 16-byte aligned).
+__device__ __forceinline__ void async_copy16s(unsigned saddr, const double *src, bool on) {
+    const int bytes = on ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(src), "r"(bytes)
+                 : "memory");
+}
+
+// ceil(a / b) for b > 0 and any sign of a.
+__device__ __forceinline__ long long ceil_div(long long a, long long b) {
+    const long long q = a / b;
+    return q + ((a % b != 0) && (a > 0));
+}
+
 __device__ __forceinline__ void async_copy_wait() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
@@ -166,10 +185,11 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane >> 4, l16 = lane & (L - 1);
-    const UnitParams U = units[blockIdx.y];
-    const IsoUnit I = iso_units[(size_t)blockIdx.y * V.niso + iso];
+    // blockIdx.x = unit (fastest): the CTAs in flight share a tile of K in L2
+    const UnitParams U = units[blockIdx.x];
+    const IsoUnit I = iso_units[(size_t)blockIdx.x * V.niso + iso];
     const int S = V.tstride;
-    const int ms = blockIdx.x * kDenseTile;
+    const int ms = blockIdx.y * kDenseTile;
     const int m_end = min(ms + kDenseTile, min(V.nwave, U.mcount));   // exclusive
     if (ms >= m_end) return;
     const int orow = (warp * 2 + grp) * J;       // first output of this half-warp within the tile
@@ -246,22 +266,65 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
             const short4 win = active ? s_win[r] : make_short4(0, 0, 0, 0);
             __syncthreads();   // the previous block's tiles are fully consumed
 
-            // (2)+(3) stage the tiles with asynchronous 8-byte copies (LDGSTS): all rows of a
-            // warp are in flight at once, a masked element is zero-filled (source size 0).
+            // (2)+(3) stage the tiles with asynchronous copies (LDGSTS): all rows of a warp are
+            // in flight at once, a masked element is zero-filled (source size 0).  The masks are
+            // row ranges computed once per block, the addresses advance by a constant.
             //   W: the unit's profile on the sub-cell offsets of this block, zero outside each
             //      offset's window (reference layout: consecutive r are consecutive samples);
-            //   K: the dense strengths, masked to the Doppler segment.
-            for (int t = warp * 2 + grp; t < wrows; t += kDenseWarps * 2) {
-                const int d = w_lo + t;
-                const bool on = active && d >= win.x && d < win.y;
-                const double *src = on ? prof + ((long long)half - r + (long long)S * d) : prof;
-                async_copy8(&Ws[t][l16], src, on);
+            {
+                const int t0 = warp * 2 + grp;
+                const int wa = win.x - w_lo, wn_rows = active ? win.y - win.x : 0;   // rows on
+                const double *src = prof + ((long long)half - r + (long long)S * (w_lo + t0));
+                const long long step = (long long)S * (kDenseWarps * 2);
+                unsigned dst = (unsigned)__cvta_generic_to_shared(&Ws[t0][l16]);
+                for (int t = t0; t < wrows; t += kDenseWarps * 2) {
+                    const bool on = (unsigned)(t - wa) < (unsigned)wn_rows;
+                    async_copy8s(dst, on ? src : prof, on);
+                    src += step;
+                    dst += kDenseWarps * 2 * L * 8;
+                }
             }
-            for (int t = warp * 2 + grp; t < krows; t += kDenseWarps * 2) {
-                const int c = c_lo + t;
-                const long long cell = (long long)c * S + r;
-                const bool on = active && c >= 0 && cell >= sa && cell < sb;
-                async_copy8(&Ks[t][l16], on ? kd + cell : kd, on);
+            //   K: the dense strengths, masked to the Doppler segment.  Two sub-cell offsets per
+            //      thread (16-byte copies) when the rows are 16-byte aligned (S even).
+            if ((S & 1) == 0) {
+                const int pr = lane & 7;                       // pair of offsets 2*pr, 2*pr + 1
+                const int t0 = warp * 4 + (lane >> 3);         // 4 rows per warp instruction
+                const int r2 = rb * L + 2 * pr;
+                // rows t with sa <= (c_lo + t)*S + r < sb and c_lo + t >= 0, for r2 and r2 + 1
+                const long long base = (long long)c_lo * S + r2;
+                int lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+                if (r2 < S) {
+                    const long long a = max(sa, 0LL);
+                    lo0 = (int)max(0LL, ceil_div(a - base, S));
+                    hi0 = (int)min((long long)krows, ceil_div(sb - base, S));
+                    lo1 = (int)max(0LL, ceil_div(a - base - 1, S));
+                    hi1 = (int)min((long long)krows, ceil_div(sb - base - 1, S));
+                    if (c_lo < 0) {
+                        lo0 = max(lo0, -c_lo);
+                        lo1 = max(lo1, -c_lo);
+                    }
+                }
+                const double *src = kd + (base + (long long)S * t0);
+                const long long step = (long long)S * (kDenseWarps * 4);
+                unsigned dst = (unsigned)__cvta_generic_to_shared(&Ks[t0][2 * pr]);
+                for (int t = t0; t < krows; t += kDenseWarps * 4) {
+                    const bool on0 = t >= lo0 && t < hi0, on1 = t >= lo1 && t < hi1;
+                    if (on0 == on1) {
+                        async_copy16s(dst, on0 ? src : kd, on0);
+                    } else {
+                        async_copy8s(dst, on0 ? src : kd, on0);
+                        async_copy8s(dst + 8, on1 ? src + 1 : kd, on1);
+                    }
+                    src += step;
+                    dst += kDenseWarps * 4 * L * 8;
+                }
+            } else {
+                for (int t = warp * 2 + grp; t < krows; t += kDenseWarps * 2) {
+                    const int c = c_lo + t;
+                    const long long cell = (long long)c * S + r;
+                    const bool on = active && c >= 0 && cell >= sa && cell < sb;
+                    async_copy8(&Ks[t][l16], on ? kd + cell : kd, on);
+                }
             }
             // anomaly bits of the K rows: thread i of the CTA takes rows i, i + 256, ...
             for (int t = threadIdx.x; t < krows; t += blockDim.x) {
@@ -376,7 +439,7 @@ int launch_accumulate_dense(cudaStream_t st, const StaticView &V, int nunits,
     const int ntiles = (V.nwave + kDenseTile - 1) / kDenseTile;
     for (int u0 = 0; u0 < nunits; u0 += 65535) {
         const int nu = nunits - u0 < 65535 ? nunits - u0 : 65535;
-        dim3 grid((unsigned)ntiles, (unsigned)nu);
+        dim3 grid((unsigned)nu, (unsigned)ntiles);
         accumulate_dense_kernel<<<grid, kDenseWarps * 32, smem, st>>>(
             V, units + u0, iso_units + (size_t)u0 * V.niso, iso, row, nrows, kd, bounds, abits,
             abits_words, cutoff, out, err);

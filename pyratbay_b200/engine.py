@@ -236,7 +236,8 @@ class Engine:
         ms = np.zeros(5, np.float64)
         check(self._lib.pb200_engine_last_timing(self._h, _dp(ms)))
         return {"strengths_ms": ms[0], "accumulate_ms": ms[1], "h2d_ms": ms[2],
-                "d2h_ms": ms[3], "total_ms": ms[4]}
+                "d2h_ms": ms[3], "total_ms": ms[4], "dense_ms": self.dense_ms(),
+                "dense_units": self.dense_units()}
 
     def launch_count(self):
         return int(self._lib.pb200_engine_launch_count(self._h))

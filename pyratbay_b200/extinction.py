@@ -97,7 +97,8 @@ def compute_opacity(pyrat, write=True, host='rank0', nchunks=4):
         ex._assembler = None                        # release the old buffers first
         asm = ex._assembler = parallel.TableAssembler(
             n_units, ex.nwave, owners, rank, device=pyrat.device, nchunks=nchunks)
-    ex.timing = {'strengths_ms': 0.0, 'accumulate_ms': 0.0, 'total_ms': 0.0}
+    ex.timing = {'strengths_ms': 0.0, 'accumulate_ms': 0.0, 'total_ms': 0.0, 'dense_ms': 0.0,
+                 'dense_units': 0}
     for c, units, ptr in asm.chunks():
         if len(units):
             extinction(pyrat, units, grid=True, add=False, out_device_ptr=ptr)
