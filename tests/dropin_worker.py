@@ -51,7 +51,7 @@ def main():
 
     # constant-R table (2-point interpolation path)
     with open("opacity_R.cfg", "w") as f:
-        f.write(base + "logfile = outputs/table_R.log\nresolution = 15000.0\n")
+        f.write(base + "logfile = outputs/table_R.log\nresolution = 15000.0\nwnstep = 1.0\n")
     out["etable_R"] = pb.run("opacity_R.cfg").ex.etable
 
     # forward model through the reference's Line_By_Line (forked workers, add=1) and get_ec
