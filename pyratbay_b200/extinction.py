@@ -91,32 +91,99 @@ def compute_opacity(pyrat, write=True, host='rank0', nchunks=4):
             ex.temp[idx // ex.nlayers], ex.press[idx % ex.nlayers],
             pyrat.atm.vmr[idx % ex.nlayers])
     owners = parallel.unit_owners(n_units, world, cost, equal_counts=True)
+    if write and host == 'none':
+        host = 'rank0'
+    to_host = host == 'all' or (host == 'rank0' and rank == 0)
+    stream_out = world == 1 and to_host             # rows leave the device chunk by chunk
+    want_chunks = nchunks if (world > 1 or stream_out) else 1
     asm = getattr(ex, '_assembler', None)
-    if asm is None or (asm.n_units, asm.nwave, asm.world) != (n_units, ex.nwave, world) \
+    if asm is None or (asm.n_units, asm.nwave, asm.world, asm.want_chunks) != \
+            (n_units, ex.nwave, world, want_chunks) \
             or any(not np.array_equal(a, b) for a, b in zip(asm.owners, owners)):
         ex._assembler = None                        # release the old buffers first
         asm = ex._assembler = parallel.TableAssembler(
-            n_units, ex.nwave, owners, rank, device=pyrat.device, nchunks=nchunks)
+            n_units, ex.nwave, owners, rank, device=pyrat.device, nchunks=want_chunks,
+            align=ex.nlayers if world == 1 else 1)
+        asm.want_chunks = want_chunks
     ex.timing = {'strengths_ms': 0.0, 'accumulate_ms': 0.0, 'total_ms': 0.0, 'dense_ms': 0.0,
                  'dense_units': 0}
-    for c, units, ptr in asm.chunks():
-        if len(units):
-            extinction(pyrat, units, grid=True, add=False, out_device_ptr=ptr)
-            for key in ex.timing:
-                ex.timing[key] += float(pyrat.last_timing[key])
-        asm.publish(c)
-    table = asm.finish()
+    if to_host and (getattr(ex, 'etable', None) is None
+                    or ex.etable.shape != (ex.ntemp, ex.nlayers, ex.nwave)):
+        ex.etable = pinned_zeros((ex.ntemp, ex.nlayers, ex.nwave))
+
+    # With one rank the rows are final as soon as a chunk is computed: a helper thread copies
+    # them to the host and appends them to the .npz while the next chunk is on the GPU (the
+    # engine call and the file write both release the GIL).
+    drain = _RowDrain(pyrat, cs_file if write else None) if stream_out else None
+    try:
+        for c, units, ptr in asm.chunks():
+            if len(units):
+                extinction(pyrat, units, grid=True, add=False, out_device_ptr=ptr)
+                for key in ex.timing:
+                    ex.timing[key] += pyrat.last_timing[key]
+            asm.publish(c)
+            if drain is not None and len(units):
+                drain.put(asm.local, asm.bounds[c], asm.bounds[c] + len(units))
+        table = asm.finish()
+    finally:
+        if drain is not None:
+            drain.close()
     ex.etable_dev = table.view(ex.ntemp, ex.nlayers, ex.nwave)
 
-    if write and host == 'none':
-        host = 'rank0'
-    if host == 'all' or (host == 'rank0' and rank == 0):
-        if getattr(ex, 'etable', None) is None or ex.etable.shape != tuple(ex.etable_dev.shape):
-            ex.etable = pinned_zeros(ex.etable_dev.shape)
+    if to_host and not stream_out:
         torch.from_numpy(ex.etable).copy_(ex.etable_dev)     # one D2H into pinned memory
     if write and rank == 0:
-        io.write_opacity(cs_file, ex.species, ex.temp, ex.press, ex.wn, ex.etable)
+        if not stream_out:
+            io.write_opacity(cs_file, ex.species, ex.temp, ex.press, ex.wn, ex.etable)
         log.head(f"Cross-section table written to file: '{cs_file}'.", indent=2)
+
+
+class _RowDrain:
+    """Helper thread of compute_opacity: device rows -> pinned `ex.etable` -> .npz member."""
+
+    def __init__(self, pyrat, cs_file):
+        import queue
+        import threading
+        import torch
+        ex = pyrat.ex
+        self.flat = torch.from_numpy(ex.etable).view(-1, ex.nwave)
+        self.stream = torch.cuda.Stream(device=torch.device('cuda', pyrat.device))
+        self.writer = (io.OpacityWriter(cs_file, ex.species, ex.temp, ex.press, ex.wn)
+                       if cs_file is not None else None)
+        self.queue = queue.Queue()
+        self.error = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def put(self, rows_dev, lo, hi):
+        self.queue.put((rows_dev, lo, hi))
+
+    def _run(self):
+        import torch
+        try:
+            while True:
+                item = self.queue.get()
+                if item is None:
+                    return
+                rows_dev, lo, hi = item
+                with torch.cuda.stream(self.stream):
+                    self.flat[lo:hi].copy_(rows_dev[lo:hi], non_blocking=True)
+                self.stream.synchronize()
+                if self.writer is not None:
+                    self.writer.write(self.flat[lo:hi].numpy())
+        except Exception as exc:   # surfaced by close()
+            self.error = exc
+
+    def close(self):
+        self.queue.put(None)
+        self.thread.join()
+        if self.writer is not None:
+            if self.error is None:
+                self.writer.close()
+            else:
+                self.writer.__exit__(type(self.error), self.error, None)
+        if self.error is not None:
+            raise self.error
 
 
 def extinction(pyrat, indices, grid=False, add=False, skip_mol=[], out_device_ptr=None):

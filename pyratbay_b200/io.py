@@ -27,6 +27,65 @@ def write_opacity(ofile, species, temp, press, wn, opacity):
     )
 
 
+class OpacityWriter:
+    """Write an opacity table file incrementally: same members and layout as write_opacity
+    (np.savez, io.py:570-606), but the `opacity` array [ntemp, nlayers, nwave] is streamed row
+    block by row block, so the file can be written while later rows are still being computed.
+
+        with OpacityWriter(ofile, species, temp, press, wn) as w:
+            w.write(rows)            # any number of consecutive [*, nwave] row blocks
+    """
+
+    def __init__(self, ofile, species, temp, press, wn):
+        import zipfile
+        if not isinstance(species, str):
+            raise ValueError("'species' input must be a string")
+        if not ofile.endswith('.npz'):
+            ofile += '.npz'                      # as np.savez does
+        self.shape = (len(temp), len(press), len(wn))
+        self._left = int(np.prod(self.shape)) * 8
+        self._zf = zipfile.ZipFile(ofile, 'w', zipfile.ZIP_STORED, allowZip64=True)
+        for name, arr in (('species', [species]), ('temperature', temp), ('pressure', press),
+                          ('wavenumber', wn)):
+            self._member(name, np.asanyarray(arr))
+        self._f = self._zf.open('opacity.npy', 'w', force_zip64=True)
+        np.lib.format.write_array_header_1_0(
+            self._f, {'descr': '<f8', 'fortran_order': False, 'shape': self.shape})
+
+    def _member(self, name, arr):
+        with self._zf.open(name + '.npy', 'w', force_zip64=True) as f:
+            np.lib.format.write_array(f, arr, allow_pickle=True)
+
+    def write(self, rows):
+        rows = np.ascontiguousarray(rows, '<f8')
+        self._left -= rows.nbytes
+        if self._left < 0:
+            raise ValueError('OpacityWriter: more rows than the table holds')
+        self._f.write(memoryview(rows).cast('B'))
+
+    def close(self):
+        if self._zf is None:
+            return
+        self._f.close()
+        self._member('units', np.asanyarray(dict(_UNITS)))
+        self._zf.close()
+        self._zf = None
+        if self._left != 0:
+            raise ValueError('OpacityWriter: the table was not written completely')
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is None:
+            self.close()
+        elif self._zf is not None:
+            self._f.close()
+            self._zf.close()
+            self._zf = None
+        return False
+
+
 def read_opacity(ofile, extract='all'):
     """Read an opacity table (io.py:609-694).  extract in {'arrays','opacity','all'}."""
     if ofile.endswith('petitRADTRANS.h5'):

@@ -79,13 +79,14 @@ class TableAssembler:
     `finish()` returns the complete table [n_units, nwave] on the device of EVERY rank.  No
     host bounce and no padding copy: the engine writes straight into the buffer the collective
     reads; slots are padded to a common row count (`equal_counts` partitions differ by at
-    most one row).  With one rank the slot buffer is the table.
+    most one row).  With one rank the slot buffer is the table (chunks then only serve the
+    caller's own pipelining: finished rows are written out while the next ones are computed).
 
     Reference analogue: the shared `mp.Array` that the forked workers of
     pyratbay/pyrat/extinction.py:100-122 fill (and line_sampling.py:253-275 for the consumer).
     """
 
-    def __init__(self, n_units, nwave, owners, rank, device=None, nchunks=4):
+    def __init__(self, n_units, nwave, owners, rank, device=None, nchunks=4, align=1):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -99,8 +100,13 @@ class TableAssembler:
         else:
             self.dev = torch.device('cuda', device)
         pad = max(len(o) for o in self.owners)
-        nchunks = max(1, min(int(nchunks), pad)) if self.world > 1 else 1
-        self.bounds = [int(b) for b in np.linspace(0, pad, nchunks + 1).round()]
+        nchunks = max(1, min(int(nchunks), pad))
+        # chunk boundaries in slot rows, optionally on multiples of `align` (one rank: whole
+        # temperatures per chunk, so that no strengths pass is computed twice)
+        bounds = np.linspace(0, pad, nchunks + 1)
+        bounds = np.round(bounds / align) * align if align > 1 else np.round(bounds)
+        bounds[0], bounds[-1] = 0, pad
+        self.bounds = sorted(set(int(b) for b in np.clip(bounds, 0, pad)))
         self.local = torch.empty((pad, self.nwave), dtype=torch.float64, device=self.dev)
         self.pending = []
         if self.world == 1:
@@ -108,7 +114,7 @@ class TableAssembler:
             return
         self.table = torch.empty((self.n_units, self.nwave), dtype=torch.float64, device=self.dev)
         self.stage, self.src, self.dst = [], [], []
-        for c in range(nchunks):
+        for c in range(len(self.bounds) - 1):
             lo, hi = self.bounds[c], self.bounds[c + 1]
             rows = hi - lo
             self.stage.append(torch.empty((self.world, rows, self.nwave), dtype=torch.float64,
