@@ -80,8 +80,8 @@ __device__ __forceinline__ void async_copy_wait() {
 }
 
 size_t dense_smem_bytes() {
-    return sizeof(double) * kDenseLanes * (kKRows + kWRows) + sizeof(unsigned short) * kKRows +
-           sizeof(short4) * kDenseMaxStride;
+    return sizeof(double) * kDenseLanes * (kKRows + kWRows) +
+           sizeof(unsigned short) * kKRows * kMaxMerge + sizeof(short4) * kDenseMaxStride;
 }
 
 __global__ void __launch_bounds__(256)
@@ -109,6 +109,28 @@ densify_kernel(StaticView V, long long gbeg, long long gend, const double *__res
     const double k = ks[g];
     if (k < kthr) return;  // :265
     kd[V.g_iown[g]] = k;
+}
+
+__global__ void __launch_bounds__(256)
+merge_minor_kernel(StaticView V, long long gbeg, long long gend, const double *__restrict__ ks,
+                   const unsigned long long *__restrict__ kmax_entry, double ethresh, double adop,
+                   const int *__restrict__ main_bounds, double *__restrict__ kd,
+                   double *__restrict__ kd_all) {
+    extern __shared__ double s_dop[];
+    for (int i = threadIdx.x; i < V.ndop; i += blockDim.x)
+        s_dop[i] = V.dop_thr ? V.dop_thr[i] : V.doppler[i];
+    __syncthreads();
+    const long long g = gbeg + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= gend) return;
+    const double kthr = dmul(ethresh, __longlong_as_double((long long)*kmax_entry));
+    const double k = ks[g];
+    if (k < kthr) return;  // :265
+    const int idop = V.ndop >= 2 ? doppler_index(V, s_dop, dmul(adop, V.g_wn[g])) : 0;  // :278
+    const int cell = V.g_iown[g];
+    if (main_bounds[idop] <= cell && cell < main_bounds[idop + 1]) {
+        kd[cell] = k;
+        kd_all[cell] = dadd(kd_all[cell], k);   // one group per cell and isotope: no race
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -171,29 +193,35 @@ __device__ __forceinline__ void dense_steps(const double *__restrict__ kp,
 // under 100 KB, so two CTAs share an SM: one stages while the other computes.
 __global__ void __launch_bounds__(kDenseWarps * 32, 2)
 accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
-                        const IsoUnit *__restrict__ iso_units, int iso, int row, int nrows,
-                        const double *__restrict__ kd, const int *__restrict__ bounds,
-                        const unsigned *__restrict__ abits, long long abits_words, double cutoff,
-                        double *__restrict__ out, int *__restrict__ err) {
+                        const IsoUnit *__restrict__ iso_units, DenseSet D, int row, int nrows,
+                        long long abits_words, double cutoff, double *__restrict__ out,
+                        int *__restrict__ err) {
     constexpr int L = kDenseLanes;
     extern __shared__ double s_dyn[];
     double (*Ks)[L] = reinterpret_cast<double (*)[L]>(s_dyn);     // [kKRows]: cell c_lo + t
     double (*Ws)[L] = Ks + kKRows;                                // [kWRows]: offset w_lo + t
-    unsigned short *As = reinterpret_cast<unsigned short *>(Ws + kWRows);   // [kKRows] anomaly bits
-    short4 *s_win = reinterpret_cast<short4 *>(As + kKRows);      // [S] windows per sub-cell offset
+    // anomaly bits of the K rows, one plane of kKRows entries per isotope of the set
+    unsigned short *As = reinterpret_cast<unsigned short *>(Ws + kWRows);
+    short4 *s_win = reinterpret_cast<short4 *>(As + kMaxMerge * kKRows);   // [S] windows
     __shared__ int s_dmin, s_dmax;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane >> 4, l16 = lane & (L - 1);
     // blockIdx.x = unit (fastest): the CTAs in flight share a tile of K in L2
     const UnitParams U = units[blockIdx.x];
+    const int iso = D.iso[0];
     const IsoUnit I = iso_units[(size_t)blockIdx.x * V.niso + iso];
+    // a merged unit convolves the sum plane and corrects every isotope's anomalous cells
+    const bool merged_unit = (U.aslot & kMergedUnitBit) != 0;
+    const int nset = merged_unit ? D.n : 1;
+    const double *__restrict__ kd = merged_unit ? D.kd_all : D.kd[0];
+    const int *__restrict__ bounds = D.bounds;
+    const long long slot_off = (long long)(U.aslot & ~kMergedUnitBit) * abits_words;
     const int S = V.tstride;
     const int ms = blockIdx.y * kDenseTile;
     const int m_end = min(ms + kDenseTile, min(V.nwave, U.mcount));   // exclusive
     if (ms >= m_end) return;
     const int orow = (warp * 2 + grp) * J;       // first output of this half-warp within the tile
-    const unsigned *__restrict__ ab = abits + (long long)U.aslot * abits_words;
 
     double acc[J];
 #pragma unroll
@@ -326,16 +354,24 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
                     async_copy8(&Ks[t][l16], on ? kd + cell : kd, on);
                 }
             }
-            // anomaly bits of the K rows: thread i of the CTA takes rows i, i + 256, ...
-            for (int t = threadIdx.x; t < krows; t += blockDim.x) {
-                const int c = c_lo + t;
-                const long long cell0 = (long long)c * S + rb * L;
-                unsigned bits = 0u;
-                if (c >= 0 && cell0 < V.onwn) {
+            // anomaly bits of the K rows (only blocks with an offset whose anomalous window
+            // differs need them): thread i of the CTA takes rows i, i + 256, ...
+            const bool fix = __syncthreads_or(active && (win.z != win.x || win.w != win.y));
+            if (fix) {
+                for (int t = threadIdx.x; t < krows; t += blockDim.x) {
+                    const int c = c_lo + t;
+                    const long long cell0 = (long long)c * S + rb * L;
+                    const bool in = c >= 0 && cell0 < V.onwn;
                     const long long wi = cell0 >> 5;
-                    bits = __funnelshift_r(ab[wi], ab[wi + 1], (unsigned)(cell0 & 31));
+                    for (int q = 0; q < nset; q++) {
+                        unsigned bits = 0u;
+                        if (in) {
+                            const unsigned *ab = D.abits[q] + slot_off;
+                            bits = __funnelshift_r(ab[wi], ab[wi + 1], (unsigned)(cell0 & 31));
+                        }
+                        As[q * kKRows + t] = (unsigned short)(bits & 0xffffu);
+                    }
                 }
-                As[t] = (unsigned short)(bits & 0xffffu);
             }
             async_copy_wait();
             __syncthreads();
@@ -360,7 +396,7 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
 
             // (5) anomalous cells of this block: add the samples their window has and the
             //     regular one lacks, remove the opposite (at most one output at either end).
-            if (active && (win.z != win.x || win.w != win.y)) {
+            if (fix && active && (win.z != win.x || win.w != win.y)) {
 #pragma unroll 1
                 for (int part = 0; part < 2; part++) {
                     const int a = part ? min(win.y, win.w) : min(win.x, win.z);
@@ -375,9 +411,18 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
                         double pv = prof[pi];
                         if (in_n) pv = -pv;
                         const int t0 = orow + (dmax - 1) - d;   // K row of output 0's cell
+                        // the strength of the anomalous GROUP (the tile holds the sum over the
+                        // merged isotopes): from the isotope's own array, masked like the tile
+                        for (int q = 0; q < nset; q++) {
+                            const unsigned short *aq = As + q * kKRows + t0;
+                            const double *__restrict__ kq = D.kd[q];
 #pragma unroll
-                        for (int x = 0; x < J; x++)
-                            if ((As[t0 + x] >> l16) & 1u) acc[x] = fma(Ks[t0 + x][l16], pv, acc[x]);
+                            for (int x = 0; x < J; x++)
+                                if ((aq[x] >> l16) & 1u) {
+                                    const long long cell = (long long)(c_lo + t0 + x) * S + r;
+                                    if (cell >= sa && cell < sb) acc[x] = fma(kq[cell], pv, acc[x]);
+                                }
+                        }
                     }
                 }
             }
@@ -428,10 +473,22 @@ int launch_segment_bounds(cudaStream_t st, const StaticView &V, long long gbeg, 
     return 0;
 }
 
+int launch_merge_minor(cudaStream_t st, const StaticView &V, long long gbeg, long long gend,
+                       const double *ksum_tp, const unsigned long long *kmax_entry,
+                       double ethresh, double adop, const int *main_bounds, double *kd,
+                       double *kd_all) {
+    if (gend <= gbeg) return 0;
+    const unsigned blocks = (unsigned)((gend - gbeg + 255) / 256);
+    merge_minor_kernel<<<blocks, 256, sizeof(double) * V.ndop, st>>>(
+        V, gbeg, gend, ksum_tp, kmax_entry, ethresh, adop, main_bounds, kd, kd_all);
+    PB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_accumulate_dense(cudaStream_t st, const StaticView &V, int nunits,
-                            const UnitParams *units, const IsoUnit *iso_units, int iso, int row,
-                            int nrows, const double *kd, const int *bounds, const unsigned *abits,
-                            long long abits_words, double cutoff, double *out, int *err) {
+                            const UnitParams *units, const IsoUnit *iso_units,
+                            const DenseSet &set, int row, int nrows, long long abits_words,
+                            double cutoff, double *out, int *err) {
     if (nunits == 0 || V.nwave == 0) return 0;
     const size_t smem = dense_smem_bytes();
     PB_CUDA(cudaFuncSetAttribute(accumulate_dense_kernel,
@@ -441,8 +498,8 @@ int launch_accumulate_dense(cudaStream_t st, const StaticView &V, int nunits,
         const int nu = nunits - u0 < 65535 ? nunits - u0 : 65535;
         dim3 grid((unsigned)nu, (unsigned)ntiles);
         accumulate_dense_kernel<<<grid, kDenseWarps * 32, smem, st>>>(
-            V, units + u0, iso_units + (size_t)u0 * V.niso, iso, row, nrows, kd, bounds, abits,
-            abits_words, cutoff, out, err);
+            V, units + u0, iso_units + (size_t)u0 * V.niso, set, row, nrows, abits_words, cutoff,
+            out, err);
         PB_CUDA(cudaGetLastError());
     }
     return 0;

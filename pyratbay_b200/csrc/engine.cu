@@ -194,7 +194,9 @@ struct pb200_engine {
     // dense-convolution accumulate path (dense_kernels.cu)
     std::vector<long long> iso_gbeg, iso_gend;   // group range of every isotope
     DevBuf<double> d_kd;                         // dense strengths of one (T, isotope) [onwn]
+    DevBuf<double> d_kd_pool;                    // sum plane + one array per merged minor isotope
     DevBuf<int> d_bounds, d_dense_err;           // Doppler segments [ndop+1]; error flag
+    DevBuf<int> d_bounds_main;                   // main isotope's segments of every pass of a chunk
     struct DenseIso {
         DevBuf<unsigned> abits;                  // [ndivs][words] anomaly bitmask per ofactor
         std::vector<char> built;                 // per divisor slot
@@ -930,6 +932,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
             reach += 2LL * ofactor + 2;
             I.reach = (int)std::min<long long>(reach, 0x7fffffffLL);
             I.dense_from = 0x7fffffff;
+            I.merged = 0;
         }
         // distinct (T, Z) -> strengths pass
         std::vector<double> key(1 + niso);
@@ -995,8 +998,9 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
     // PB200_DENSE_MIN_OCC sets the occupancy threshold (groups / fine samples, default 0.25:
     // the gather path delivers ~2.6e12 samples/s, the dense one ~1.4e13 MAC/s over all cells).
     int rc = 0;
-    std::vector<int> dense_isos;
-    std::vector<char> unit_dense(n_units, 0);
+    std::vector<int> dense_isos, minor_isos;
+    int main_iso = -1;
+    std::vector<char> unit_dense(n_units, 0), unit_merged(n_units, 0);
     e->dense_unit_isos = 0;
     e->dense_ms = 0.0;
     {
@@ -1058,6 +1062,43 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
             }
             if (!any) dense_isos.clear();
         }
+        // Minor isotopes of the main isotope's species are merged into its dense plane where
+        // they select the same profile (same Lorentz sample for the unit, same Doppler sample
+        // on the cell): the convolution costs the same whatever number of isotopes it sums,
+        // and the gather kernels are left with the cells where the Doppler samples differ.
+        // PB200_DENSE_MERGE=0 keeps every minor isotope on the gather path.
+        if (!dense_isos.empty()) {
+            const char *me = std::getenv("PB200_DENSE_MERGE");
+            main_iso = dense_isos[0];
+            for (int di : dense_isos)
+                if (e->iso_gend[di] - e->iso_gbeg[di] > e->iso_gend[main_iso] - e->iso_gbeg[main_iso])
+                    main_iso = di;
+            if (!(me && std::strcmp(me, "0") == 0))
+                for (int i = 0; i < niso && (int)minor_isos.size() < kMaxMerge - 1; i++) {
+                    if (std::find(dense_isos.begin(), dense_isos.end(), i) != dense_isos.end())
+                        continue;
+                    if (iso_row[i] == iso_row[main_iso] && e->iso_imol[i] == e->iso_imol[main_iso] &&
+                        e->iso_gend[i] > e->iso_gbeg[i])
+                        minor_isos.push_back(i);
+                }
+            bool any_merged = false;
+            for (int u = 0; u < n_units && !minor_isos.empty(); u++) {
+                const IsoUnit &M = iso_units[(size_t)u * niso + main_iso];
+                if (!unit_dense[u] || M.dense_from == 0x7fffffff) continue;
+                bool same = true;
+                for (int mi : minor_isos)
+                    same = same && iso_units[(size_t)u * niso + mi].ilor == M.ilor;
+                if (!same) continue;
+                for (int mi : minor_isos) {
+                    IsoUnit &I = iso_units[(size_t)u * niso + mi];
+                    I.dense_from = M.dense_from;
+                    I.merged = 1;
+                }
+                unit_merged[u] = 1;
+                any_merged = true;
+            }
+            if (!any_merged) minor_isos.clear();
+        }
         if (!dense_isos.empty()) {
             // anomaly bitmasks of the ofactors in use (static per line list: built once)
             const long long words = (onwn >> 5) + 2;
@@ -1067,7 +1108,9 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
             PB_CUDA(cudaMemsetAsync(e->d_dense_err.p, 0, sizeof(int), st));
             const StaticView V0 = e->view();
             bool built_any = false;
-            for (int di : dense_isos) {
+            std::vector<int> bit_isos(dense_isos);
+            bit_isos.insert(bit_isos.end(), minor_isos.begin(), minor_isos.end());
+            for (int di : bit_isos) {
                 pb200_engine::DenseIso &D = e->dense_iso[di];
                 if (D.built.empty()) {
                     rc = D.abits.alloc((size_t)ndivs * (size_t)words);
@@ -1096,14 +1139,24 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
                     e->dense_off = true;
                     e->dense_iso.clear();
                     dense_isos.clear();
+                    minor_isos.clear();
                     std::fill(unit_dense.begin(), unit_dense.end(), 0);
+                    std::fill(unit_merged.begin(), unit_merged.end(), 0);
+                    for (IsoUnit &I : iso_units) {
+                        I.dense_from = 0x7fffffff;
+                        I.merged = 0;
+                    }
                 }
             }
         }
         if (!dense_isos.empty()) {
             rc = e->d_kd.alloc((size_t)onwn);
             if (!rc) rc = e->d_bounds.alloc((size_t)ndop + 1);
+            if (!rc && !minor_isos.empty())
+                rc = e->d_kd_pool.alloc((1 + minor_isos.size()) * (size_t)onwn);
             if (rc) return rc;
+            for (int u = 0; u < n_units; u++)
+                if (unit_merged[u]) units[u].aslot |= kMergedUnitBit;
         }
     }
 
@@ -1261,6 +1314,27 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         if (rc) return rc;
         if (V.ngroups > 0) e->launches++;
         PB_CUDA(cudaEventRecord(e->ev[2], st));
+        // merged minor isotopes: the gather kernels need the main isotope's Doppler segments
+        // of every strengths pass of this chunk
+        const int *p_main_bounds = nullptr;
+        if (!minor_isos.empty()) {
+            rc = e->d_bounds_main.alloc((size_t)ntc * (ndop + 1));
+            if (rc) return rc;
+            std::vector<double> pass_adop(ntc, 0.0);
+            std::vector<char> have(ntc, 0);
+            for (size_t a = 0; a < cu.size(); a++) {
+                pass_adop[cu[a].tpass] = ci[a * niso + main_iso].adop;
+                have[cu[a].tpass] = 1;
+            }
+            for (int t = 0; t < ntc; t++) {
+                if (!have[t]) continue;
+                rc = launch_segment_bounds(st, V, e->iso_gbeg[main_iso], e->iso_gend[main_iso],
+                                           pass_adop[t], e->d_bounds_main.p + (size_t)t * (ndop + 1));
+                if (rc) return rc;
+                e->launches++;
+            }
+            p_main_bounds = e->d_bounds_main.p;
+        }
         // one launch per run of equal mode; grid.y is limited to 65535 units per launch
         for (size_t u0 = 0; u0 < cu.size();) {
             size_t u1 = u0;
@@ -1285,7 +1359,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
             rc = launch_accumulate(st, V, nu, p_units + u0, p_iso_units + u0 * niso,
                                    p_iso_row, e->d_ksum.p,
                                    e->d_kmax.p, nrows, ethresh, cutoff, cmode[u0] & 15, d_out,
-                                   ksplit, e->d_partial.p, chunked);
+                                   ksplit, e->d_partial.p, chunked, p_main_bounds);
             if (rc) return rc;
             e->launches += ksplit > 1 ? 2 : 1;
             if (counters) {
@@ -1316,25 +1390,56 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
             size_t b = a;
             while (b < cu.size() && (cmode[b] & 16) && cu[b].tpass == cu[a].tpass) b++;
             const long long words = (onwn >> 5) + 2;
+            const int tpass = cu[a].tpass;
+            const double *ks_t = e->d_ksum.p + (size_t)tpass * (size_t)e->ngroups;
             for (int di : dense_isos) {
                 const int row = iso_row[di];
+                const unsigned long long *kmax_t = e->d_kmax.p + (size_t)tpass * nrows + row;
                 PB_CUDA(cudaMemsetAsync(e->d_kd.p, 0, sizeof(double) * (size_t)onwn, st));
-                rc = launch_densify(st, V, e->iso_gbeg[di], e->iso_gend[di],
-                                    e->d_ksum.p + (size_t)cu[a].tpass * (size_t)e->ngroups,
-                                    e->d_kmax.p + (size_t)cu[a].tpass * nrows + row, ethresh,
+                rc = launch_densify(st, V, e->iso_gbeg[di], e->iso_gend[di], ks_t, kmax_t, ethresh,
                                     e->d_kd.p);
-                if (!rc)
+                if (rc) return rc;
+                DenseSet set;
+                set.n = 1;
+                set.iso[0] = di;
+                set.kd[0] = e->d_kd.p;
+                set.abits[0] = e->dense_iso[di].abits.p;
+                set.kd_all = e->d_kd.p;
+                set.bounds = e->d_bounds.p;
+                if (di == main_iso && !minor_isos.empty()) {
+                    // sum plane = main plane + the minor isotopes' groups that share its profile
+                    const int *mb = p_main_bounds + (size_t)tpass * (ndop + 1);
+                    double *pool = e->d_kd_pool.p;
+                    PB_CUDA(cudaMemcpyAsync(pool, e->d_kd.p, sizeof(double) * (size_t)onwn,
+                                            cudaMemcpyDeviceToDevice, st));
+                    PB_CUDA(cudaMemsetAsync(pool + onwn, 0,
+                                            sizeof(double) * minor_isos.size() * (size_t)onwn, st));
+                    for (size_t j = 0; j < minor_isos.size(); j++) {
+                        const int mi = minor_isos[j];
+                        rc = launch_merge_minor(st, V, e->iso_gbeg[mi], e->iso_gend[mi], ks_t, kmax_t,
+                                                ethresh, ci[a * niso + mi].adop, mb,
+                                                pool + (j + 1) * (size_t)onwn, pool);
+                        if (rc) return rc;
+                        e->launches++;
+                        set.iso[set.n] = mi;
+                        set.kd[set.n] = pool + (j + 1) * (size_t)onwn;
+                        set.abits[set.n] = e->dense_iso[mi].abits.p;
+                        set.n++;
+                    }
+                    set.kd_all = pool;
+                    set.bounds = mb;
+                } else {
                     rc = launch_segment_bounds(st, V, e->iso_gbeg[di], e->iso_gend[di],
                                                ci[a * niso + di].adop, e->d_bounds.p);
-                if (!rc)
-                    rc = launch_accumulate_dense(st, V, (int)(b - a), p_units + a,
-                                                 p_iso_units + a * niso, di, row, nrows,
-                                                 e->d_kd.p, e->d_bounds.p,
-                                                 e->dense_iso[di].abits.p, words, cutoff, d_out,
-                                                 e->d_dense_err.p);
+                    if (rc) return rc;
+                    e->launches++;
+                }
+                rc = launch_accumulate_dense(st, V, (int)(b - a), p_units + a,
+                                             p_iso_units + a * niso, set, row, nrows, words,
+                                             cutoff, d_out, e->d_dense_err.p);
                 if (rc) return rc;
-                e->launches += 3;
-                e->dense_unit_isos += (int64_t)(b - a);
+                e->launches += 2;
+                e->dense_unit_isos += (int64_t)(b - a) * set.n;
             }
             a = b;
         }

@@ -125,6 +125,10 @@ struct IsoUnit {
     // `dense_from` go through the gather kernels, the others through the dense convolution
     // (INT_MAX: all gathered, the default; dense_kernels.cu).
     int dense_from;
+    // 1: a minor isotope merged into the dense plane of the main one (dense_kernels.cu): its
+    // groups at or above dense_from that select the SAME Doppler sample as the main isotope
+    // does on their cell are in that plane; the gather kernels take the others.
+    int merged;
 };
 
 }  // namespace pb200

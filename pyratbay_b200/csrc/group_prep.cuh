@@ -76,11 +76,12 @@ template <int MODE>
 __device__ __forceinline__ bool prepare_group(const StaticView &V, const UnitParams &U,
                                               const IsoUnit &I, const double *s_dop,
                                               double kthr, double cutoff, double w, int iown,
-                                              double k, Prep *out) {
+                                              double k, Prep *out, int *idop_out = nullptr) {
     if (k < kthr) return false;  // :265 skip weak lines
     k = dmul(k, I.dens);         // :271-272 (dens == 1 when add == 0)
     const int idwn = dynamic_index(V, U, w);                                         // :275
     const int idop = (V.ndop >= 2) ? doppler_index(V, s_dop, dmul(I.adop, w)) : 0;  // :278
+    if (idop_out) *idop_out = idop;
     const int at = I.ilor * V.ndop + idop;
     const ProfileSlot ps = load_slot((MODE == kTransposed ? V.tslot : V.pslot) + at);
     const int half = ps.half;
@@ -103,6 +104,14 @@ __device__ __forceinline__ bool prepare_group(const StaticView &V, const UnitPar
         out->hi = jhi;
     }
     return true;
+}
+
+// True when a group of a MERGED minor isotope (IsoUnit::merged) is evaluated by the dense
+// kernel: it sits at or above dense_from and selects the Doppler sample the main isotope's
+// lines select on its cell (`main_bounds`: the main isotope's segments of this strengths pass).
+__device__ __forceinline__ bool in_dense_plane(const IsoUnit &I, const int *__restrict__ main_bounds,
+                                               int iown, int idop) {
+    return iown >= I.dense_from && main_bounds[idop] <= iown && iown < main_bounds[idop + 1];
 }
 
 }  // namespace pb200

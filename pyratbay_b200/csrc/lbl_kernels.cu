@@ -171,7 +171,7 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
                   const double *__restrict__ ksum,
                   const unsigned long long *__restrict__ kmax, int nrows, double ethresh,
                   double cutoff, double *__restrict__ out, int ksplit,
-                  double *__restrict__ partial) {
+                  double *__restrict__ partial, const int *__restrict__ dense_bounds) {
     extern __shared__ double s_doppler[];  // [ndop]
     // One staged group per lane: {k, byte address of its sample for coordinate 0} and
     // {first coordinate, number of coordinates}.
@@ -270,9 +270,17 @@ accumulate_kernel(StaticView V, const UnitParams *__restrict__ units,
                 }
                 Prep p;
                 p.k = 0.0; p.base = 0; p.lo = 0; p.hi = 0;
-                if (g < ghi && cur_iown < I.dense_from)
-                    prepare_group<MODE>(V, U, I, s_doppler, kthr, cutoff, cur_w, cur_iown, cur_k,
-                                        &p);
+                // cells at or above dense_from belong to the dense kernel, except the groups
+                // of a merged isotope that select another Doppler sample than the main one
+                if (g < ghi && (cur_iown < I.dense_from || I.merged)) {
+                    int idop = 0;
+                    const bool ok = prepare_group<MODE>(V, U, I, s_doppler, kthr, cutoff, cur_w,
+                                                        cur_iown, cur_k, &p, &idop);
+                    if (ok && I.merged &&
+                        in_dense_plane(I, dense_bounds + (size_t)U.tpass * (V.ndop + 1), cur_iown, idop)) {
+                        p.k = 0.0; p.lo = 0; p.hi = 0;
+                    }
+                }
                 // clip to the coordinates this warp owns so that empty slots cost nothing more
                 const int lo = max(p.lo, xmin), hi = min(p.hi, xmax + 1);
                 const int n = min(32, ghi - c);
@@ -549,8 +557,10 @@ __device__ __forceinline__ bool candidate_range(const StaticView &V, const UnitP
     if (fhi < 0 || flo > V.onwn - 1) return false;
     if (flo < 0) flo = 0;
     if (fhi > V.onwn - 1) fhi = V.onwn - 1;
-    if (flo >= I.dense_from) return false;   // those cells belong to the dense kernel
-    if (fhi >= I.dense_from) fhi = I.dense_from - 1;
+    if (!I.merged) {
+        if (flo >= I.dense_from) return false;   // those cells belong to the dense kernel
+        if (fhi >= I.dense_from) fhi = I.dense_from - 1;
+    }
     const int *gb = V.gbin + (size_t)iso * (V.nbins + 1);
     *glo = gb[V.fd_binw.div((int)flo)];
     *ghi = gb[V.fd_binw.div((int)fhi) + 1];
@@ -567,7 +577,7 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                          const double *__restrict__ ksum,
                          const unsigned long long *__restrict__ kmax, int nrows, double ethresh,
                          double cutoff, double *__restrict__ out, int ksplit,
-                         double *__restrict__ partial) {
+                         double *__restrict__ partial, const int *__restrict__ dense_bounds) {
     // dynamic shared memory: [8][kChunkTile] per-warp private copies of the tile, then the
     // Doppler thresholds [ndop]
     extern __shared__ double s_dyn[];
@@ -648,9 +658,16 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                 Prep p;
                 p.k = 0.0; p.base = 0; p.lo = 0; p.hi = 0;
                 bool valid = false;
-                if (g < gend && cur_iown < I.dense_from)   // cells >= dense_from: dense kernel
+                // cells >= dense_from: dense kernel, except the groups of a merged isotope
+                // that select another Doppler sample than the main isotope does there
+                if (g < gend && (cur_iown < I.dense_from || I.merged)) {
+                    int idop = 0;
                     valid = prepare_group<kTransposed>(V, U, I, s_doppler, kthr, cutoff, cur_w,
-                                                       cur_iown, cur_k, &p);
+                                                       cur_iown, cur_k, &p, &idop);
+                    if (valid && I.merged)
+                        valid = !in_dense_plane(I, dense_bounds + (size_t)U.tpass * (V.ndop + 1),
+                                                cur_iown, idop);
+                }
                 const int lo = max(p.lo, m0), hi = min(p.hi, tile_hi);
                 valid = valid && hi > lo;
                 const unsigned vb = __ballot_sync(0xffffffffu, valid);
@@ -943,7 +960,7 @@ int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
                       const UnitParams *units, const IsoUnit *iso_units, const int *iso_row,
                       const double *ksum, const unsigned long long *kmax, int nrows,
                       double ethresh, double cutoff, int mode, double *out, int ksplit,
-                      double *partial, int chunked) {
+                      double *partial, int chunked, const int *dense_bounds) {
     if (nunits == 0 || V.nwave == 0) return 0;
     if (ksplit < 1 || !partial) ksplit = 1;
     const int tile_w = (mode == kTransposed && chunked) ? kChunkTile : kTileOutputs;
@@ -963,16 +980,20 @@ int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
             PB_CUDA(cudaFuncSetAttribute(wide ? wide_k : narrow_k,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
         (wide ? wide_k : narrow_k)<<<grid, 256, csmem, st>>>(
-            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
+            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial,
+            dense_bounds);
     } else if (mode == kLinterp)
         accumulate_kernel<kLinterp><<<grid, 256, smem, st>>>(
-            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
+            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial,
+            dense_bounds);
     else if (mode == kTransposed)
         accumulate_kernel<kTransposed><<<grid, 256, smem, st>>>(
-            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
+            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial,
+            dense_bounds);
     else
         accumulate_kernel<kStrided><<<grid, 256, smem, st>>>(
-            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial);
+            V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial,
+            dense_bounds);
     PB_CUDA(cudaGetLastError());
     if (ksplit > 1) {
         dim3 rgrid((unsigned)((V.nwave + 255) / 256), (unsigned)nunits, (unsigned)nrows);

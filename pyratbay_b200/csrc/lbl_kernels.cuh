@@ -19,7 +19,7 @@ int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
                       const UnitParams *units, const IsoUnit *iso_units, const int *iso_row,
                       const double *ksum, const unsigned long long *kmax, int nrows,
                       double ethresh, double cutoff, int mode, double *out, int ksplit,
-                      double *partial, int chunked);
+                      double *partial, int chunked, const int *dense_bounds = nullptr);
 
 // mode values of launch_accumulate
 constexpr int kModeStrided = 0, kModeLinterp = 1, kModeTransposed = 2;

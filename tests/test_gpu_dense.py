@@ -107,7 +107,9 @@ def test_dense_main_isotope_gather_for_the_rest(monkeypatch):
     got = eng.extinction_batch(temps, dens, isoz, iext, 2, case.ethresh, 0, 0)
     used = eng.dense_units()
     eng.close()
-    assert 0 < used <= len(temps)
+    # the main isotope on its own plane, isotope 2 (same output row) merged into it where it
+    # selects the same profile: at most two isotopes per unit on the dense path
+    assert 0 < used <= 2 * len(temps)
     want, _ = _oracle(case, temps, dens, isoz, 0, iso_iext=iext, nextinct=2)
     assert got.shape == want.shape
     assert _peak_err(got, want) < TOL_PEAK
@@ -160,3 +162,34 @@ def test_near_integer_cutoff_steps_stay_on_the_gather_path(monkeypatch):
     eng.close()
     want, _ = _oracle(case, temps, dens, isoz, 0)
     assert _peak_err(got, want) < TOL_PEAK
+
+
+@pytest.mark.parametrize("min_span", ["1", "24"])
+@pytest.mark.parametrize("merge", ["1", "0"])
+def test_minor_isotopes_merged_into_the_main_plane(min_span, merge, monkeypatch):
+    """One dense plane for the main isotope plus the minor isotopes of the same species where
+    they select the same Voigt profile; the cells where their Doppler sample differs from the
+    main isotope's, and narrow footprints, stay with the gather kernels.  Same results as the
+    oracle with identical counters, with and without merging."""
+    case = helpers.synthetic_case(nlines=150_000, wnlow=9000.0, wnhigh=9400.0, wnstep=0.25,
+                                  wnosamp=360, cutoff=10.07, extent=60.0, nlayers=9, ndop=40)
+    temps, dens = case.atm.temp, case.atm.d
+    isoz = helpers.partition(case, temps).T
+    nfine = len(case.spec.own)
+    occ = np.bincount(case.isoid, minlength=4) / nfine
+    monkeypatch.setenv("PB200_DENSE_MIN_OCC", f"{0.5 * (occ[0] + occ[1]) * 0.8:.5f}")
+    monkeypatch.setenv("PB200_DENSE_MIN_SPAN", min_span)
+    monkeypatch.setenv("PB200_DENSE_MERGE", merge)
+    for add in (0, 1):
+        eng = _engine(case)
+        got, cnt = eng.extinction_batch(temps, dens, isoz, case.iso_mol_index, 1, case.ethresh,
+                                        add, 0, counters=True)
+        used = eng.dense_units()
+        eng.close()
+        want, wcnt = _oracle(case, temps, dens, isoz, add)
+        assert np.array_equal(cnt[:, :4], wcnt)
+        assert _peak_err(got, want) < TOL_PEAK
+        if merge == "1":
+            assert used > len(temps)          # more than the main isotope took the dense path
+        else:
+            assert 0 < used <= len(temps)
