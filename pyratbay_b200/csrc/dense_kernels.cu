@@ -69,10 +69,12 @@ __device__ __forceinline__ void async_copy16s(unsigned saddr, const double *src,
                  : "memory");
 }
 
-// ceil(a / b) for b > 0 and any sign of a.
-__device__ __forceinline__ long long ceil_div(long long a, long long b) {
-    const long long q = a / b;
-    return q + ((a % b != 0) && (a > 0));
+// min(rows, max(0, ceil(x / S))): the first row t of a tile with S*t >= x, without a 64-bit
+// division (fd divides non-negative 31-bit numbers by S exactly).
+__device__ __forceinline__ int first_row(long long x, int rows, int S, const FastDiv &fd) {
+    if (x <= 0) return 0;
+    if (x >= (long long)rows * S) return rows;
+    return fd.div_ceil((int)x);
 }
 
 __device__ __forceinline__ void async_copy_wait() {
@@ -323,10 +325,10 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
                 int lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
                 if (r2 < S) {
                     const long long a = max(sa, 0LL);
-                    lo0 = (int)max(0LL, ceil_div(a - base, S));
-                    hi0 = (int)min((long long)krows, ceil_div(sb - base, S));
-                    lo1 = (int)max(0LL, ceil_div(a - base - 1, S));
-                    hi1 = (int)min((long long)krows, ceil_div(sb - base - 1, S));
+                    lo0 = first_row(a - base, krows, S, V.fd_tstride);
+                    hi0 = first_row(sb - base, krows, S, V.fd_tstride);
+                    lo1 = first_row(a - base - 1, krows, S, V.fd_tstride);
+                    hi1 = first_row(sb - base - 1, krows, S, V.fd_tstride);
                     if (c_lo < 0) {
                         lo0 = max(lo0, -c_lo);
                         lo1 = max(lo1, -c_lo);

@@ -660,14 +660,18 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                 bool valid = false;
                 // cells >= dense_from: dense kernel, except the groups of a merged isotope
                 // that select another Doppler sample than the main isotope does there
-                if (g < gend && (cur_iown < I.dense_from || I.merged)) {
-                    int idop = 0;
-                    valid = prepare_group<kTransposed>(V, U, I, s_doppler, kthr, cutoff, cur_w,
-                                                       cur_iown, cur_k, &p, &idop);
-                    if (valid && I.merged)
-                        valid = !in_dense_plane(I, dense_bounds + (size_t)U.tpass * (V.ndop + 1),
-                                                cur_iown, idop);
+                bool mine = g < gend && (cur_iown < I.dense_from || I.merged);
+                if (mine && I.merged && cur_iown >= I.dense_from) {
+                    // the Doppler sample first (:278, cheap): most groups of a merged isotope
+                    // are in the dense plane and need no further preparation
+                    const int idop =
+                        V.ndop >= 2 ? doppler_index(V, s_doppler, dmul(I.adop, cur_w)) : 0;
+                    mine = !in_dense_plane(I, dense_bounds + (size_t)U.tpass * (V.ndop + 1),
+                                           cur_iown, idop);
                 }
+                if (mine)
+                    valid = prepare_group<kTransposed>(V, U, I, s_doppler, kthr, cutoff, cur_w,
+                                                       cur_iown, cur_k, &p);
                 const int lo = max(p.lo, m0), hi = min(p.hi, tile_hi);
                 valid = valid && hi > lo;
                 const unsigned vb = __ballot_sync(0xffffffffu, valid);
