@@ -14,3 +14,15 @@ def pinned_zeros(shape):
     except Exception:
         pass
     return np.zeros(shape, np.double)
+
+
+def pinned_empty(shape):
+    """Like pinned_zeros without the fill (for buffers that are overwritten completely)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.empty(tuple(int(s) for s in shape), dtype=torch.float64,
+                               pin_memory=True).numpy()
+    except Exception:
+        pass
+    return np.empty(shape, np.double)

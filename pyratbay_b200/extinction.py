@@ -9,7 +9,7 @@ import numpy as np
 from . import constants as pc
 from . import io
 from . import parallel
-from ._mem import pinned_zeros
+from ._mem import pinned_empty
 
 
 def compute_opacity(pyrat, write=True, host='rank0', nchunks=4):
@@ -107,9 +107,12 @@ def compute_opacity(pyrat, write=True, host='rank0', nchunks=4):
         asm.want_chunks = want_chunks
     ex.timing = {'strengths_ms': 0.0, 'accumulate_ms': 0.0, 'total_ms': 0.0, 'dense_ms': 0.0,
                  'dense_units': 0}
-    if to_host and (getattr(ex, 'etable', None) is None
-                    or ex.etable.shape != (ex.ntemp, ex.nlayers, ex.nwave)):
-        ex.etable = pinned_zeros((ex.ntemp, ex.nlayers, ex.nwave))
+    need_etable = to_host and (getattr(ex, 'etable', None) is None
+                               or ex.etable.shape != (ex.ntemp, ex.nlayers, ex.nwave))
+    if need_etable and not stream_out:
+        ex.etable = pinned_empty((ex.ntemp, ex.nlayers, ex.nwave))
+    elif need_etable:
+        ex.etable = None            # allocated by the drain thread while the first chunk computes
 
     # With one rank the rows are final as soon as a chunk is computed: a helper thread copies
     # them to the host and appends them to the .npz while the next chunk is on the GPU (the
@@ -146,10 +149,10 @@ class _RowDrain:
         import threading
         import torch
         ex = pyrat.ex
-        self.flat = torch.from_numpy(ex.etable).view(-1, ex.nwave)
-        self.stream = torch.cuda.Stream(device=torch.device('cuda', pyrat.device))
-        self.writer = (io.OpacityWriter(cs_file, ex.species, ex.temp, ex.press, ex.wn)
-                       if cs_file is not None else None)
+        self.ex = ex
+        self.cs_file = cs_file
+        self.device = torch.device('cuda', pyrat.device)
+        self.writer = None
         self.queue = queue.Queue()
         self.error = None
         self.thread = threading.Thread(target=self._run, daemon=True)
@@ -161,6 +164,15 @@ class _RowDrain:
     def _run(self):
         import torch
         try:
+            # page-locking 0.8 GB takes a few 0.1 s: done here, behind the first chunk's compute
+            ex = self.ex
+            torch.cuda.set_device(self.device)
+            if ex.etable is None:
+                ex.etable = pinned_empty((ex.ntemp, ex.nlayers, ex.nwave))
+            self.flat = torch.from_numpy(ex.etable).view(-1, ex.nwave)
+            self.stream = torch.cuda.Stream(device=self.device)
+            if self.cs_file is not None:
+                self.writer = io.OpacityWriter(self.cs_file, ex.species, ex.temp, ex.press, ex.wn)
             while True:
                 item = self.queue.get()
                 if item is None:
