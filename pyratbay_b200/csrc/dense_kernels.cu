@@ -39,6 +39,7 @@
 #include "group_prep.cuh"
 
 #include <climits>
+#include <cstdlib>
 
 namespace pb200 {
 
@@ -448,6 +449,291 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
     }
 }
 
+// Warp-specialised form of the same kernel: ONE CTA per SM with two tile buffers; two producer
+// warps stage block rb+1 (LDGSTS) while the eight consumer warps convolve block rb, so the
+// FMA pipe does not wait for tile staging.  Hand-off through named barriers: full[b] (the
+// producers arrive, the consumers wait), empty[b] (the other way round).  Everything else --
+// windows, masks, walk, corrections, summation order -- is the code of accumulate_dense_kernel.
+constexpr int kWsConsumers = kDenseWarps * 32;          // 256 threads
+constexpr int kWsProducers = 64;                        // two warps
+constexpr int kWsThreads = kWsConsumers + kWsProducers;
+
+__device__ __forceinline__ void named_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+size_t dense_ws_smem_bytes() {
+    return 2 * (sizeof(double) * kDenseLanes * (kKRows + kWRows) +
+                sizeof(unsigned short) * kKRows * kMaxMerge) +
+           sizeof(short4) * kDenseMaxStride;
+}
+
+__global__ void __launch_bounds__(kWsThreads, 1)
+accumulate_dense_ws_kernel(StaticView V, const UnitParams *__restrict__ units,
+                           const IsoUnit *__restrict__ iso_units, DenseSet D, int row, int nrows,
+                           long long abits_words, double cutoff, double *__restrict__ out,
+                           int *__restrict__ err) {
+    constexpr int L = kDenseLanes;
+    extern __shared__ double s_dyn[];
+    // two buffers of {K tile, W tile, anomaly bits}, then the window table
+    constexpr size_t kBufDoubles = (size_t)L * (kKRows + kWRows) + (kKRows * kMaxMerge) / 4;
+    short4 *s_win = reinterpret_cast<short4 *>(s_dyn + 2 * kBufDoubles);
+    __shared__ int s_dmin, s_dmax;
+    __shared__ int s_fix[2];
+
+    const bool producer = threadIdx.x >= kWsConsumers;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane >> 4, l16 = lane & (L - 1);
+    const UnitParams U = units[blockIdx.x];
+    const int iso = D.iso[0];
+    const IsoUnit I = iso_units[(size_t)blockIdx.x * V.niso + iso];
+    const bool merged_unit = (U.aslot & kMergedUnitBit) != 0;
+    const int nset = merged_unit ? D.n : 1;
+    const double *__restrict__ kd = merged_unit ? D.kd_all : D.kd[0];
+    const int *__restrict__ bounds = D.bounds;
+    const long long slot_off = (long long)(U.aslot & ~kMergedUnitBit) * abits_words;
+    const int S = V.tstride;
+    const int ms = blockIdx.y * kDenseTile;
+    const int m_end = min(ms + kDenseTile, min(V.nwave, U.mcount));   // exclusive
+    if (ms >= m_end) return;
+    const int orow = (warp * 2 + grp) * J;       // consumers: first output of this half-warp
+
+    double acc[J];
+#pragma unroll
+    for (int x = 0; x < J; x++) acc[x] = 0.0;
+
+    const long long reach_cells = I.reach / S + 2;
+    const long long flo = max(0LL, ((long long)ms - reach_cells) * S);
+    const long long fhi = min(V.onwn, ((long long)m_end + reach_cells) * S);
+    const int c_ref = U.mcount >> 1;
+
+    for (int seg = 0; seg < V.ndop; seg++) {
+        const long long sa = max((long long)bounds[seg], (long long)I.dense_from);
+        const long long sb = bounds[seg + 1];
+        if (sb <= sa || sb <= flo || sa >= fhi) continue;         // CTA-uniform
+        const ProfileSlot ps = load_slot(V.pslot + I.ilor * V.ndop + seg);
+        const int half = ps.half;
+        const double *__restrict__ prof = V.profile + ps.base;
+
+        // (1) windows of every sub-cell offset (all threads)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_dmin = INT_MAX;
+            s_dmax = INT_MIN;
+        }
+        __syncthreads();
+        for (int r = threadIdx.x; r < S; r += blockDim.x) {
+            const int iown = c_ref * S + r;
+            const int idwn0 = U.fd_ofactor.div(iown);
+            int jlo, jhi, mlo, mhi, alo, ahi;
+            dynamic_range(U, cutoff, half, iown, idwn0, &jlo, &jhi);
+            output_range(U, jlo, jhi, &mlo, &mhi);
+            alo = mlo;
+            ahi = mhi;
+            if (iown - idwn0 * U.ofactor == 0) {
+                dynamic_range(U, cutoff, half, iown, idwn0 - 1, &jlo, &jhi);
+                output_range(U, jlo, jhi, &alo, &ahi);
+            }
+            if (mhi <= mlo) mlo = mhi = c_ref;
+            if (ahi <= alo) alo = ahi = c_ref;
+            s_win[r] = make_short4((short)(mlo - c_ref), (short)(mhi - c_ref),
+                                   (short)(alo - c_ref), (short)(ahi - c_ref));
+            if (mhi > mlo || ahi > alo) {
+                const int lo = (mhi > mlo ? (ahi > alo ? min(mlo, alo) : mlo) : alo) - c_ref;
+                const int hi = (mhi > mlo ? (ahi > alo ? max(mhi, ahi) : mhi) : ahi) - c_ref;
+                atomicMin(&s_dmin, lo);
+                atomicMax(&s_dmax, hi);
+            }
+        }
+        __syncthreads();
+        const int dmin = s_dmin, dmax = s_dmax;
+        if (dmax <= dmin) continue;
+        if (dmax - dmin > kDenseSpanMax || dmin < -30000 || dmax > 30000) {
+            if (threadIdx.x == 0) atomicExch(err, 1);
+            continue;
+        }
+
+        const int c_lo = ms - (dmax - 1);
+        const int w_lo = dmin - J;
+        const int nsteps = J + (dmax - dmin) - 1;
+        const int krows = kDenseTile - J + nsteps;
+        const int wrows = dmax + J - w_lo;
+        const int nrb = (S + L - 1) / L;
+
+        if (producer) {
+            const int pt = threadIdx.x - kWsConsumers;             // 0..63
+            for (int rb = 0; rb < nrb; rb++) {
+                const int b = rb & 1;
+                double (*Ks)[L] = reinterpret_cast<double (*)[L]>(s_dyn + b * kBufDoubles);
+                double (*Ws)[L] = Ks + kKRows;
+                unsigned short *As = reinterpret_cast<unsigned short *>(Ws + kWRows);
+                if (rb >= 2) named_sync(3 + b, kWsThreads);       // buffer b released
+                // W tile: 4 rows per pass of the 64 threads
+                {
+                    const int r = rb * L + (pt & 15);
+                    const bool active = r < S;
+                    const short4 win = active ? s_win[r] : make_short4(0, 0, 0, 0);
+                    const bool fix =
+                        __any_sync(0xffffffffu, active && (win.z != win.x || win.w != win.y));
+                    if (pt == 0) s_fix[b] = fix;
+                    const int t0 = pt >> 4;
+                    const int wa = win.x - w_lo, wn_rows = active ? win.y - win.x : 0;
+                    const double *src = prof + ((long long)half - r + (long long)S * (w_lo + t0));
+                    const long long step = (long long)S * 4;
+                    unsigned dst = (unsigned)__cvta_generic_to_shared(&Ws[t0][pt & 15]);
+                    for (int t = t0; t < wrows; t += 4) {
+                        const bool on = (unsigned)(t - wa) < (unsigned)wn_rows;
+                        async_copy8s(dst, on ? src : prof, on);
+                        src += step;
+                        dst += 4 * L * 8;
+                    }
+                    // anomaly bits of the K rows (only blocks with a differing window)
+                    if (fix) {
+                        for (int t = pt; t < krows; t += kWsProducers) {
+                            const int c = c_lo + t;
+                            const long long cell0 = (long long)c * S + rb * L;
+                            const bool in = c >= 0 && cell0 < V.onwn;
+                            const long long wi = cell0 >> 5;
+                            for (int q = 0; q < nset; q++) {
+                                unsigned bits = 0u;
+                                if (in) {
+                                    const unsigned *ab = D.abits[q] + slot_off;
+                                    bits = __funnelshift_r(ab[wi], ab[wi + 1], (unsigned)(cell0 & 31));
+                                }
+                                As[q * kKRows + t] = (unsigned short)(bits & 0xffffu);
+                            }
+                        }
+                    }
+                }
+                // K tile: 8 rows per pass (16-byte copies), or 4 rows with 8-byte copies
+                if ((S & 1) == 0) {
+                    const int pr = pt & 7;
+                    const int t0 = pt >> 3;
+                    const int r2 = rb * L + 2 * pr;
+                    const long long base = (long long)c_lo * S + r2;
+                    int lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+                    if (r2 < S) {
+                        const long long a = max(sa, 0LL);
+                        lo0 = first_row(a - base, krows, S, V.fd_tstride);
+                        hi0 = first_row(sb - base, krows, S, V.fd_tstride);
+                        lo1 = first_row(a - base - 1, krows, S, V.fd_tstride);
+                        hi1 = first_row(sb - base - 1, krows, S, V.fd_tstride);
+                        if (c_lo < 0) {
+                            lo0 = max(lo0, -c_lo);
+                            lo1 = max(lo1, -c_lo);
+                        }
+                    }
+                    const double *src = kd + (base + (long long)S * t0);
+                    const long long step = (long long)S * 8;
+                    unsigned dst = (unsigned)__cvta_generic_to_shared(&Ks[t0][2 * pr]);
+                    for (int t = t0; t < krows; t += 8) {
+                        const bool on0 = t >= lo0 && t < hi0, on1 = t >= lo1 && t < hi1;
+                        if (on0 == on1) {
+                            async_copy16s(dst, on0 ? src : kd, on0);
+                        } else {
+                            async_copy8s(dst, on0 ? src : kd, on0);
+                            async_copy8s(dst + 8, on1 ? src + 1 : kd, on1);
+                        }
+                        src += step;
+                        dst += 8 * L * 8;
+                    }
+                } else {
+                    const int r = rb * L + (pt & 15);
+                    for (int t = pt >> 4; t < krows; t += 4) {
+                        const int c = c_lo + t;
+                        const long long cell = (long long)c * S + r;
+                        const bool on = r < S && c >= 0 && cell >= sa && cell < sb;
+                        async_copy8(&Ks[t][pt & 15], on ? kd + cell : kd, on);
+                    }
+                }
+                async_copy_wait();
+                __threadfence_block();
+                named_arrive(1 + b, kWsThreads);                   // buffer b is full
+            }
+        } else {
+            for (int rb = 0; rb < nrb; rb++) {
+                const int b = rb & 1;
+                double (*Ks)[L] = reinterpret_cast<double (*)[L]>(s_dyn + b * kBufDoubles);
+                double (*Ws)[L] = Ks + kKRows;
+                const unsigned short *As = reinterpret_cast<const unsigned short *>(Ws + kWRows);
+                const int r = rb * L + l16;
+                const bool active = r < S;
+                const short4 win = active ? s_win[r] : make_short4(0, 0, 0, 0);
+                named_sync(1 + b, kWsThreads);                     // wait until buffer b is full
+                const bool fix = s_fix[b] != 0;
+
+                // (4) the convolution
+                {
+                    double w[J];
+#pragma unroll
+                    for (int x = 1; x < J; x++) w[x] = Ws[(dmax - 1 + x) - w_lo][l16];
+                    w[0] = 0.0;
+                    const double *kp = &Ks[orow][l16];
+                    const double *wp = &Ws[(dmax - 1) - w_lo][l16];
+                    int n = 0;
+                    for (; n + J <= nsteps; n += J) {
+                        dense_steps<0>(kp, wp, w, acc, J);
+                        kp += J * L;
+                        wp -= J * L;
+                    }
+                    dense_steps<0>(kp, wp, w, acc, nsteps - n);
+                }
+
+                // (5) anomalous cells of this block
+                if (fix && active && (win.z != win.x || win.w != win.y)) {
+#pragma unroll 1
+                    for (int part = 0; part < 2; part++) {
+                        const int a = part ? min(win.y, win.w) : min(win.x, win.z);
+                        const int b2 = part ? max(win.y, win.w) : max(win.x, win.z);
+#pragma unroll 1
+                        for (int d = a; d < b2; d++) {
+                            const bool in_n = d >= win.x && d < win.y;
+                            const bool in_a = d >= win.z && d < win.w;
+                            if (in_n == in_a) continue;
+                            const long long pi = (long long)half - r + (long long)S * d;
+                            if (pi < 0 || pi > 2LL * half) continue;
+                            double pv = prof[pi];
+                            if (in_n) pv = -pv;
+                            const int t0 = orow + (dmax - 1) - d;
+                            for (int q = 0; q < nset; q++) {
+                                const unsigned short *aq = As + q * kKRows + t0;
+                                const double *__restrict__ kq = D.kd[q];
+#pragma unroll
+                                for (int x = 0; x < J; x++)
+                                    if ((aq[x] >> l16) & 1u) {
+                                        const long long cell = (long long)(c_lo + t0 + x) * S + r;
+                                        if (cell >= sa && cell < sb)
+                                            acc[x] = fma(kq[cell], pv, acc[x]);
+                                    }
+                            }
+                        }
+                    }
+                }
+                if (rb + 2 < nrb) named_arrive(3 + b, kWsThreads);  // buffer b may be refilled
+            }
+        }
+    }
+
+    if (producer) return;
+    // (6) sum the 16 sub-cell offsets of a half-warp and add to the output row
+    double mine = 0.0;
+#pragma unroll
+    for (int x = 0; x < J; x++) {
+        double v = acc[x];
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (l16 == x) mine = v;
+    }
+    mine = dmul(mine, I.dens);
+    if (ms + orow + l16 < m_end) {
+        double *dst = out + ((size_t)U.out_index * nrows + row) * (size_t)V.nwave;
+        dst[ms + orow + l16] += mine;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 int launch_anomaly_bits(cudaStream_t st, const StaticView &V, long long gbeg, long long gend,
                         const UnitParams &U, unsigned *bits, int *err) {
@@ -492,16 +778,29 @@ int launch_accumulate_dense(cudaStream_t st, const StaticView &V, int nunits,
                             const DenseSet &set, int row, int nrows, long long abits_words,
                             double cutoff, double *out, int *err) {
     if (nunits == 0 || V.nwave == 0) return 0;
-    const size_t smem = dense_smem_bytes();
-    PB_CUDA(cudaFuncSetAttribute(accumulate_dense_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // PB200_DENSE_WS=0 selects the two-CTAs-per-SM form (one stages while the other computes)
+    // instead of the warp-specialised one (producer warps + double-buffered tiles).
+    const char *env = std::getenv("PB200_DENSE_WS");
+    const bool ws = !(env && env[0] == '0');
+    const size_t smem = ws ? dense_ws_smem_bytes() : dense_smem_bytes();
+    if (ws)
+        PB_CUDA(cudaFuncSetAttribute(accumulate_dense_ws_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+        PB_CUDA(cudaFuncSetAttribute(accumulate_dense_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = (V.nwave + kDenseTile - 1) / kDenseTile;
     for (int u0 = 0; u0 < nunits; u0 += 65535) {
         const int nu = nunits - u0 < 65535 ? nunits - u0 : 65535;
         dim3 grid((unsigned)nu, (unsigned)ntiles);
-        accumulate_dense_kernel<<<grid, kDenseWarps * 32, smem, st>>>(
-            V, units + u0, iso_units + (size_t)u0 * V.niso, set, row, nrows, abits_words, cutoff,
-            out, err);
+        if (ws)
+            accumulate_dense_ws_kernel<<<grid, kWsThreads, smem, st>>>(
+                V, units + u0, iso_units + (size_t)u0 * V.niso, set, row, nrows, abits_words,
+                cutoff, out, err);
+        else
+            accumulate_dense_kernel<<<grid, kDenseWarps * 32, smem, st>>>(
+                V, units + u0, iso_units + (size_t)u0 * V.niso, set, row, nrows, abits_words,
+                cutoff, out, err);
         PB_CUDA(cudaGetLastError());
     }
     return 0;

@@ -65,8 +65,12 @@ CASES = [
 # such units on the gather path; test_near_integer_cutoff_steps_stay_on_the_gather_path)
 
 
+@pytest.mark.parametrize("form", ["ws", "2cta"])
 @pytest.mark.parametrize("kwargs", CASES)
-def test_dense_path_matches_oracle_and_gather(kwargs, monkeypatch):
+def test_dense_path_matches_oracle_and_gather(kwargs, form, monkeypatch):
+    # both forms of the dense kernel: warp-specialised (producer warps, double-buffered tiles)
+    # and two CTAs per SM
+    monkeypatch.setenv("PB200_DENSE_WS", "1" if form == "ws" else "0")
     case = helpers.synthetic_case(**kwargs)
     temps, dens = case.atm.temp, case.atm.d
     isoz = helpers.partition(case, temps).T
