@@ -778,10 +778,12 @@ int launch_accumulate_dense(cudaStream_t st, const StaticView &V, int nunits,
                             const DenseSet &set, int row, int nrows, long long abits_words,
                             double cutoff, double *out, int *err) {
     if (nunits == 0 || V.nwave == 0) return 0;
-    // PB200_DENSE_WS=0 selects the two-CTAs-per-SM form (one stages while the other computes)
-    // instead of the warp-specialised one (producer warps + double-buffered tiles).
+    // Default: the two-CTAs-per-SM form (one stages while the other computes).  PB200_DENSE_WS=1
+    // selects the warp-specialised one (producer warps + double-buffered tiles), measured 5 %
+    // slower on the bench table (1001 vs 953 ms): with staging fully hidden the FMA-pipe share
+    // does not rise, i.e. it is set by the walk itself.
     const char *env = std::getenv("PB200_DENSE_WS");
-    const bool ws = !(env && env[0] == '0');
+    const bool ws = env && env[0] == '1';
     const size_t smem = ws ? dense_ws_smem_bytes() : dense_smem_bytes();
     if (ws)
         PB_CUDA(cudaFuncSetAttribute(accumulate_dense_ws_kernel,

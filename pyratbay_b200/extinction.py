@@ -90,7 +90,9 @@ def compute_opacity(pyrat, write=True, host='rank0', nchunks=4):
             pyrat.voigt, spec, pyrat.atm, lbl.iso_atm_index, lbl.iso_mass,
             ex.temp[idx // ex.nlayers], ex.press[idx % ex.nlayers],
             pyrat.atm.vmr[idx % ex.nlayers])
-    owners = parallel.unit_owners(n_units, world, cost, equal_counts=True)
+    # whole temperatures per rank where the balance allows it: strengths and the dense path's
+    # per-temperature set-up are then computed for ~ntemp/world + 1 temperatures per rank
+    owners = parallel.unit_owners_by_temperature(ex.ntemp, ex.nlayers, world, cost)
     if write and host == 'none':
         host = 'rank0'
     to_host = host == 'all' or (host == 'rank0' and rank == 0)

@@ -48,6 +48,30 @@ def unit_owners(n_units, world, cost=None, equal_counts=False):
     return [np.where(owner == r)[0] for r in range(world)]
 
 
+def unit_owners_by_temperature(ntemp, nlayers, world, cost=None):
+    """Partition of a table's units (index = itemp*nlayers + ilayer) that keeps the units of a
+    temperature together: the temperatures are taken in snake order (coldest, hottest, second
+    coldest, ...: a monotonic cost trend with T averages out), their units concatenated, and the
+    sequence cut into `world` contiguous pieces of equal estimated cost.  A rank then needs the
+    line strengths (and the dense-path set-up) of ~ntemp/world + 1 temperatures instead of all of
+    them.  Returns the ascending unit indices of every rank (counts may differ by a few units)."""
+    n_units = ntemp * nlayers
+    if world <= 1:
+        return [np.arange(n_units)]
+    cost = np.ones(n_units) if cost is None else np.asarray(cost, np.double)
+    lo, hi, order = 0, ntemp - 1, []
+    while lo <= hi:
+        order.append(lo)
+        if hi != lo:
+            order.append(hi)
+        lo, hi = lo + 1, hi - 1
+    seq = np.concatenate([t * nlayers + np.arange(nlayers) for t in order])
+    cum = np.cumsum(cost[seq])
+    cuts = np.searchsorted(cum, cum[-1] * np.arange(1, world) / world, side='left') + 1
+    cuts = np.clip(cuts, 0, n_units)
+    return [np.sort(piece) for piece in np.split(seq, cuts)]
+
+
 def unit_costs(voigt, spec, atm, iso_atm_index, iso_mass, temps, press, vmr):
     """Relative cost of each (T,p) unit of a table for load balancing: the accumulate kernel's
     work per line grows with the number of output samples a line reaches, i.e. with the Voigt

@@ -318,6 +318,25 @@ def test_equal_count_partition():
     assert all(np.all(np.diff(o) > 0) for o in owners)
 
 
+def test_partition_by_temperature():
+    """The product partition of a table: contiguous pieces of a snake-ordered temperature
+    sequence -- every unit exactly once, balanced cost, few temperatures per rank."""
+    from pyratbay_b200 import parallel
+    ntemp, nlayers = 20, 51
+    p_cost = 28.0 + 32.0 * np.linspace(0, 1, nlayers) ** 2           # grows with pressure
+    cost = np.concatenate([p_cost * (1.0 + 0.02 * t) for t in range(ntemp)])   # and with T
+    for world in (2, 3, 4, 8):
+        owners = parallel.unit_owners_by_temperature(ntemp, nlayers, world, cost)
+        assert len(owners) == world
+        assert sorted(np.concatenate(owners)) == list(range(ntemp * nlayers))
+        loads = np.array([cost[o].sum() for o in owners])
+        assert loads.max() / loads.min() < 1.06
+        temps_per_rank = [len(np.unique(o // nlayers)) for o in owners]
+        assert max(temps_per_rank) <= -(-ntemp // world) + 2
+        assert all(np.all(np.diff(o) > 0) for o in owners)
+    assert len(parallel.unit_owners_by_temperature(ntemp, nlayers, 1)[0]) == ntemp * nlayers
+
+
 def test_unit_costs_balance_table_partition():
     """Cost model used to deal (T,p) units to ranks: grows with pressure (wider profiles) and
     gives a far better balance than round-robin would on cost."""
