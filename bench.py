@@ -575,7 +575,16 @@ def run_table(args):
     roofline, roofline_l2, roofline_fp64 = rooflines(
         acc_ms, int(cnt[:, 2].sum()), len(mine), nwave, int(cnt[:, 4].sum()),
         int(cnt[:, 3].sum()), int(cnt[:, 5].sum()), ms_per_step,
-        "accumulate_chunks_kernel<3,16>", "table", default, local_rank, launches_per_step)
+        "accumulate stage = accumulate_dense_kernel (dense convolution: main isotope + merged "
+        "minor isotopes) + accumulate_chunks_kernel<3,16> (gather: the remaining groups)",
+        "table", default, local_rank, launches_per_step)
+    dense_share = float(np.mean(dense_ms[:args.steps])) / acc_ms if acc_ms > 0 else 0.0
+    roofline["dense_kernel_share_of_stage"] = dense_share
+    roofline["note"] = (
+        "algorithmic HBM bytes of the whole accumulate stage over its device time.  The stage is "
+        "compute/delivery bound, not HBM bound (the algorithm needs 1.3 TB per table): the dense "
+        "kernel runs on the fp64 FMA pipe (65 % active, profiles/r02c_dense_merged.txt), the gather "
+        "kernel on L2->SM bandwidth; roofline_fp64 is the meaningful ceiling (DESIGN.md section 5)")
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:

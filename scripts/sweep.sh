@@ -19,7 +19,7 @@ launch() {   # bench.py arguments...
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
       --master-port $PORT bench.py --gpus $N --no-cpu-baseline --no-forward-detail "$@" 2>> $err | grep '^{' | tail -1 >> $out
   else
-    timeout 900 python bench.py --no-cpu-baseline --no-forward-detail "$@" 2>> $err | grep '^{' | tail -1 >> $out
+    timeout 1700 python bench.py --no-cpu-baseline --no-forward-detail "$@" 2>> $err | grep '^{' | tail -1 >> $out
   fi
 }
 for n in 100000 1000000 10000000 100000000 1000000000; do
