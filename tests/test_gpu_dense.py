@@ -197,3 +197,24 @@ def test_minor_isotopes_merged_into_the_main_plane(min_span, merge, monkeypatch)
             assert used > len(temps)          # more than the main isotope took the dense path
         else:
             assert 0 < used <= len(temps)
+
+
+def test_two_dense_planes_and_merged_minors(monkeypatch):
+    """Occupancy threshold between the second and third isotope: two isotopes get a dense plane
+    of their own, the two rarest are merged into the main one's."""
+    case = helpers.synthetic_case(nlines=150_000, wnlow=9000.0, wnhigh=9400.0, wnstep=0.25,
+                                  wnosamp=360, cutoff=10.07, extent=60.0, nlayers=7, ndop=40)
+    temps, dens = case.atm.temp, case.atm.d
+    isoz = helpers.partition(case, temps).T
+    occ = np.bincount(case.isoid, minlength=4) / len(case.spec.own)
+    monkeypatch.setenv("PB200_DENSE_MIN_OCC", f"{0.5 * (occ[1] + occ[2]) * 0.8:.5f}")
+    monkeypatch.setenv("PB200_DENSE_MIN_SPAN", "8")
+    eng = _engine(case)
+    got, cnt = eng.extinction_batch(temps, dens, isoz, case.iso_mol_index, 1, case.ethresh, 0, 0,
+                                    counters=True)
+    used = eng.dense_units()
+    eng.close()
+    want, wcnt = _oracle(case, temps, dens, isoz, 0)
+    assert np.array_equal(cnt[:, :4], wcnt)
+    assert _peak_err(got, want) < TOL_PEAK
+    assert used > 2 * len(temps)        # two planes plus merged isotopes
