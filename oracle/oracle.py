@@ -36,8 +36,9 @@ def build(force=False):
                               stdout=subprocess.DEVNULL)
     if os.path.isdir("/root/reference/src_c"):
         ref_dir = os.path.join(_HERE, "_ref")
-        have = os.path.isdir(ref_dir) and any(
-            f.startswith("_extcoeff") for f in os.listdir(ref_dir))
+        have = (os.path.isdir(ref_dir)
+                and any(f.startswith("_extcoeff") for f in os.listdir(ref_dir))
+                and os.path.isdir(os.path.join(ref_dir, "shimmed", "pyratbay", "lib")))
         if force or not have:
             subprocess.check_call([os.path.join(_HERE, "build_ref.sh")],
                                   stdout=subprocess.DEVNULL)
