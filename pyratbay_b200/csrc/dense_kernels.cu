@@ -177,6 +177,22 @@ __device__ __forceinline__ void dense_step(const double *__restrict__ kp,
     for (int x = 0; x < J; x++) acc[x] = fma(kv, w[(x - I + J) % J], acc[x]);
 }
 
+// The first J cells of a walk: at its n-th cell only the outputs x <= n are inside the widest
+// window (offset (dmax-1) + x - n < dmax), the others would multiply zero padding.
+template <int I>
+__device__ __forceinline__ void dense_steps_first(const double *__restrict__ kp,
+                                                  const double *__restrict__ wp,
+                                                  double (&w)[kDenseJ], double (&acc)[kDenseJ]) {
+    constexpr int J = kDenseJ;
+    if constexpr (I < J) {
+        const double kv = kp[I * kDenseLanes];
+        w[(J - I) % J] = wp[-I * kDenseLanes];
+#pragma unroll
+        for (int x = 0; x <= I; x++) acc[x] = fma(kv, w[(x - I + J) % J], acc[x]);
+        dense_steps_first<I + 1>(kp, wp, w, acc);
+    }
+}
+
 template <int I>
 __device__ __forceinline__ void dense_steps(const double *__restrict__ kp,
                                             const double *__restrict__ wp, double (&w)[kDenseJ],
@@ -384,11 +400,13 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
             {
                 double w[J];
 #pragma unroll
-                for (int x = 1; x < J; x++) w[x] = Ws[(dmax - 1 + x) - w_lo][l16];
-                w[0] = 0.0;
+                for (int x = 0; x < J; x++) w[x] = 0.0;   // offsets >= dmax: outside all windows
                 const double *kp = &Ks[orow][l16];
                 const double *wp = &Ws[(dmax - 1) - w_lo][l16];
-                int n = 0;
+                dense_steps_first<0>(kp, wp, w, acc);     // nsteps >= J always
+                kp += J * L;
+                wp -= J * L;
+                int n = J;
                 for (; n + J <= nsteps; n += J) {
                     dense_steps<0>(kp, wp, w, acc, J);
                     kp += J * L;
@@ -669,11 +687,13 @@ accumulate_dense_ws_kernel(StaticView V, const UnitParams *__restrict__ units,
                 {
                     double w[J];
 #pragma unroll
-                    for (int x = 1; x < J; x++) w[x] = Ws[(dmax - 1 + x) - w_lo][l16];
-                    w[0] = 0.0;
+                    for (int x = 0; x < J; x++) w[x] = 0.0;   // offsets >= dmax: outside all windows
                     const double *kp = &Ks[orow][l16];
                     const double *wp = &Ws[(dmax - 1) - w_lo][l16];
-                    int n = 0;
+                    dense_steps_first<0>(kp, wp, w, acc);     // nsteps >= J always
+                    kp += J * L;
+                    wp -= J * L;
+                    int n = J;
                     for (; n + J <= nsteps; n += J) {
                         dense_steps<0>(kp, wp, w, acc, J);
                         kp += J * L;
