@@ -193,6 +193,37 @@ __device__ __forceinline__ void dense_steps_first(const double *__restrict__ kp,
     }
 }
 
+// The last J-1 cells of a walk, entered at rotation phase P (= the number of steps the partial
+// iteration before them took): at the k-th of them only the outputs x >= k are still inside the
+// widest window.  kp / wp point at the phase-0 rows of the current iteration.
+template <int P, int K>
+__device__ __forceinline__ void dense_steps_last(const double *__restrict__ kp,
+                                                 const double *__restrict__ wp,
+                                                 double (&w)[kDenseJ], double (&acc)[kDenseJ]) {
+    constexpr int J = kDenseJ;
+    if constexpr (K < J) {
+        constexpr int N = P + K - 1;        // steps since the iteration's phase 0
+        constexpr int I = N % J;            // rotation phase of this step
+        const double kv = kp[N * kDenseLanes];
+        w[(J - I) % J] = wp[-N * kDenseLanes];
+#pragma unroll
+        for (int x = K; x < J; x++) acc[x] = fma(kv, w[(x - I + J) % J], acc[x]);
+        dense_steps_last<P, K + 1>(kp, wp, w, acc);
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void dense_last_dispatch(int phase, const double *__restrict__ kp,
+                                                    const double *__restrict__ wp,
+                                                    double (&w)[kDenseJ], double (&acc)[kDenseJ]) {
+    if constexpr (P < kDenseJ) {
+        if (phase == P)   // warp-uniform
+            dense_steps_last<P, 1>(kp, wp, w, acc);
+        else
+            dense_last_dispatch<P + 1>(phase, kp, wp, w, acc);
+    }
+}
+
 template <int I>
 __device__ __forceinline__ void dense_steps(const double *__restrict__ kp,
                                             const double *__restrict__ wp, double (&w)[kDenseJ],
@@ -403,16 +434,21 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
                 for (int x = 0; x < J; x++) w[x] = 0.0;   // offsets >= dmax: outside all windows
                 const double *kp = &Ks[orow][l16];
                 const double *wp = &Ws[(dmax - 1) - w_lo][l16];
+                // cells 0..J-1: growing triangle; cells J..span-1: all outputs; the last J-1
+                // cells: shrinking triangle (span = nsteps - (J-1) >= J, else the plain walk)
+                const int span = nsteps - (J - 1);
                 dense_steps_first<0>(kp, wp, w, acc);     // nsteps >= J always
                 kp += J * L;
                 wp -= J * L;
                 int n = J;
-                for (; n + J <= nsteps; n += J) {
+                const int full_end = span >= J ? span : nsteps;
+                for (; n + J <= full_end; n += J) {
                     dense_steps<0>(kp, wp, w, acc, J);
                     kp += J * L;
                     wp -= J * L;
                 }
-                dense_steps<0>(kp, wp, w, acc, nsteps - n);
+                dense_steps<0>(kp, wp, w, acc, full_end - n);
+                if (span >= J) dense_last_dispatch<0>(full_end - n, kp, wp, w, acc);
             }
 
             // (5) anomalous cells of this block: add the samples their window has and the
@@ -690,16 +726,21 @@ accumulate_dense_ws_kernel(StaticView V, const UnitParams *__restrict__ units,
                     for (int x = 0; x < J; x++) w[x] = 0.0;   // offsets >= dmax: outside all windows
                     const double *kp = &Ks[orow][l16];
                     const double *wp = &Ws[(dmax - 1) - w_lo][l16];
+                    // cells 0..J-1: growing triangle; cells J..span-1: all outputs; the last J-1
+                    // cells: shrinking triangle (span = nsteps - (J-1) >= J, else the plain walk)
+                    const int span = nsteps - (J - 1);
                     dense_steps_first<0>(kp, wp, w, acc);     // nsteps >= J always
                     kp += J * L;
                     wp -= J * L;
                     int n = J;
-                    for (; n + J <= nsteps; n += J) {
+                    const int full_end = span >= J ? span : nsteps;
+                    for (; n + J <= full_end; n += J) {
                         dense_steps<0>(kp, wp, w, acc, J);
                         kp += J * L;
                         wp -= J * L;
                     }
-                    dense_steps<0>(kp, wp, w, acc, nsteps - n);
+                    dense_steps<0>(kp, wp, w, acc, full_end - n);
+                    if (span >= J) dense_last_dispatch<0>(full_end - n, kp, wp, w, acc);
                 }
 
                 // (5) anomalous cells of this block
