@@ -236,6 +236,54 @@ __device__ __forceinline__ void dense_steps(const double *__restrict__ kp,
     }
 }
 
+// The walk of one half-warp over the cells that reach its J outputs: step n is cell
+// c_start + n (tile row orow + n), at which output x needs offset (dmax-1) + x - n.
+// [it_lo, it_hi) are the iterations (of J cells each) that can hold a non-zero K, warp-uniform:
+// a tile that straddles a Doppler-segment boundary walks only its side of it in each pass.
+__device__ __forceinline__ void dense_walk(const double (*Ks)[kDenseLanes],
+                                           const double (*Ws)[kDenseLanes], int orow, int l16,
+                                           int dmax, int w_lo, int nsteps, int it_lo, int it_hi,
+                                           double (&acc)[kDenseJ]) {
+    constexpr int J = kDenseJ, L = kDenseLanes;
+    const int niter = (nsteps + J - 1) / J;
+    if (it_hi <= it_lo) return;
+    double w[J];
+    if (it_lo == 0 && it_hi >= niter) {
+        // the whole walk.  cells 0..J-1: growing triangle; cells J..span-1: all outputs; the
+        // last J-1 cells: shrinking triangle (span = nsteps - (J-1) >= J, else the plain walk)
+#pragma unroll
+        for (int x = 0; x < J; x++) w[x] = 0.0;   // offsets >= dmax: outside all windows
+        const double *kp = &Ks[orow][l16];
+        const double *wp = &Ws[(dmax - 1) - w_lo][l16];
+        const int span = nsteps - (J - 1);
+        dense_steps_first<0>(kp, wp, w, acc);     // nsteps >= J always
+        kp += J * L;
+        wp -= J * L;
+        int n = J;
+        const int full_end = span >= J ? span : nsteps;
+        for (; n + J <= full_end; n += J) {
+            dense_steps<0>(kp, wp, w, acc, J);
+            kp += J * L;
+            wp -= J * L;
+        }
+        dense_steps<0>(kp, wp, w, acc, full_end - n);
+        if (span >= J) dense_last_dispatch<0>(full_end - n, kp, wp, w, acc);
+        return;
+    }
+    // part of the walk: the window registers as the iteration before it_lo would have left them
+    const int n0 = it_lo * J;
+    w[0] = 0.0;
+#pragma unroll
+    for (int x = 1; x < J; x++) w[x] = Ws[(dmax - 1 + x - n0) - w_lo][l16];
+    const double *kp = &Ks[orow + n0][l16];
+    const double *wp = &Ws[(dmax - 1) - w_lo - n0][l16];
+    for (int it = it_lo; it < it_hi; it++) {
+        dense_steps<0>(kp, wp, w, acc, min(J, nsteps - it * J));
+        kp += J * L;
+        wp -= J * L;
+    }
+}
+
 // Thread layout: a warp owns 2 x J consecutive outputs and 16 sub-cell offsets: lanes 0-15 hold
 // offsets r0..r0+15 for the first J outputs, lanes 16-31 the same offsets for the next J.  Tile
 // rows are 16 doubles (128 B); the two half-warps read two different rows per load, which is
@@ -337,6 +385,16 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
         const int krows = kDenseTile - J + nsteps;
         const int wrows = dmax + J - w_lo;
         const int nrb = (S + L - 1) / L;
+        // iterations of this half-warp's walk whose cells can lie in the segment (warp-uniform)
+        int it_lo, it_hi;
+        {
+            const int seg_c_lo = V.fd_tstride.div((int)sa), seg_c_hi = V.fd_tstride.div((int)(sb - 1));
+            const int c_start = c_lo + orow;
+            const int n_lo = max(0, seg_c_lo - c_start), n_hi = min(nsteps, seg_c_hi + 1 - c_start);
+            const bool any = n_hi > n_lo;
+            it_lo = __reduce_min_sync(0xffffffffu, any ? n_lo / J : 0x7fffffff);
+            it_hi = __reduce_max_sync(0xffffffffu, any ? (n_hi + J - 1) / J : 0);
+        }
 
         for (int rb = 0; rb < nrb; rb++) {
             const int r = rb * L + l16;
@@ -428,28 +486,7 @@ accumulate_dense_kernel(StaticView V, const UnitParams *__restrict__ units,
 
             // (4) the convolution.  At its n-th cell, output x of the half-warp needs offset
             //     (dmax-1) + x - n.
-            {
-                double w[J];
-#pragma unroll
-                for (int x = 0; x < J; x++) w[x] = 0.0;   // offsets >= dmax: outside all windows
-                const double *kp = &Ks[orow][l16];
-                const double *wp = &Ws[(dmax - 1) - w_lo][l16];
-                // cells 0..J-1: growing triangle; cells J..span-1: all outputs; the last J-1
-                // cells: shrinking triangle (span = nsteps - (J-1) >= J, else the plain walk)
-                const int span = nsteps - (J - 1);
-                dense_steps_first<0>(kp, wp, w, acc);     // nsteps >= J always
-                kp += J * L;
-                wp -= J * L;
-                int n = J;
-                const int full_end = span >= J ? span : nsteps;
-                for (; n + J <= full_end; n += J) {
-                    dense_steps<0>(kp, wp, w, acc, J);
-                    kp += J * L;
-                    wp -= J * L;
-                }
-                dense_steps<0>(kp, wp, w, acc, full_end - n);
-                if (span >= J) dense_last_dispatch<0>(full_end - n, kp, wp, w, acc);
-            }
+            dense_walk(Ks, Ws, orow, l16, dmax, w_lo, nsteps, it_lo, it_hi, acc);
 
             // (5) anomalous cells of this block: add the samples their window has and the
             //     regular one lacks, remove the opposite (at most one output at either end).
@@ -616,6 +653,16 @@ accumulate_dense_ws_kernel(StaticView V, const UnitParams *__restrict__ units,
         const int krows = kDenseTile - J + nsteps;
         const int wrows = dmax + J - w_lo;
         const int nrb = (S + L - 1) / L;
+        // iterations of this half-warp's walk whose cells can lie in the segment (warp-uniform)
+        int it_lo, it_hi;
+        {
+            const int seg_c_lo = V.fd_tstride.div((int)sa), seg_c_hi = V.fd_tstride.div((int)(sb - 1));
+            const int c_start = c_lo + orow;
+            const int n_lo = max(0, seg_c_lo - c_start), n_hi = min(nsteps, seg_c_hi + 1 - c_start);
+            const bool any = n_hi > n_lo;
+            it_lo = __reduce_min_sync(0xffffffffu, any ? n_lo / J : 0x7fffffff);
+            it_hi = __reduce_max_sync(0xffffffffu, any ? (n_hi + J - 1) / J : 0);
+        }
 
         if (producer) {
             const int pt = threadIdx.x - kWsConsumers;             // 0..63
@@ -720,28 +767,7 @@ accumulate_dense_ws_kernel(StaticView V, const UnitParams *__restrict__ units,
                 const bool fix = s_fix[b] != 0;
 
                 // (4) the convolution
-                {
-                    double w[J];
-#pragma unroll
-                    for (int x = 0; x < J; x++) w[x] = 0.0;   // offsets >= dmax: outside all windows
-                    const double *kp = &Ks[orow][l16];
-                    const double *wp = &Ws[(dmax - 1) - w_lo][l16];
-                    // cells 0..J-1: growing triangle; cells J..span-1: all outputs; the last J-1
-                    // cells: shrinking triangle (span = nsteps - (J-1) >= J, else the plain walk)
-                    const int span = nsteps - (J - 1);
-                    dense_steps_first<0>(kp, wp, w, acc);     // nsteps >= J always
-                    kp += J * L;
-                    wp -= J * L;
-                    int n = J;
-                    const int full_end = span >= J ? span : nsteps;
-                    for (; n + J <= full_end; n += J) {
-                        dense_steps<0>(kp, wp, w, acc, J);
-                        kp += J * L;
-                        wp -= J * L;
-                    }
-                    dense_steps<0>(kp, wp, w, acc, full_end - n);
-                    if (span >= J) dense_last_dispatch<0>(full_end - n, kp, wp, w, acc);
-                }
+                dense_walk(Ks, Ws, orow, l16, dmax, w_lo, nsteps, it_lo, it_hi, acc);
 
                 // (5) anomalous cells of this block
                 if (fix && active && (win.z != win.x || win.w != win.y)) {
