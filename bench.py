@@ -538,7 +538,9 @@ def run_table(args):
     _, cnt = eng.extinction_batch(unit_t, dens, ex.z[:, itemp].T, pyrat.lbl.iso_mol_index,
                                   pyrat.lbl.nspec, pyrat.lbl.ethresh, 0, 0, counters=True,
                                   out_device_ptr=asm.local.data_ptr())
-    launches_per_step = sum(1 for _c, units, _p in asm.chunks() if len(units))
+    # accumulate launches (batches) per device-timed step: one per chunk at N > 1, one at N = 1
+    # (the chunked single-rank form only serves the host-output pipelining of the e2e arm)
+    launches_per_step = sum(1 for _c, units, _p in asm.chunks() if len(units)) if world > 1 else 1
     nwave = spec.nwave
     voigt_samples = eng.profile_len()
     del table

@@ -197,6 +197,7 @@ struct pb200_engine {
     DevBuf<double> d_kd_pool;                    // sum plane + one array per merged minor isotope
     DevBuf<int> d_bounds, d_dense_err;           // Doppler segments [ndop+1]; error flag
     DevBuf<int> d_bounds_main;                   // main isotope's segments of every pass of a chunk
+    DevBuf<int> d_bounds_minor;                  // merged minor isotopes' segments [pass][minor][ndop+1]
     struct DenseIso {
         DevBuf<unsigned> abits;                  // [ndivs][words] anomaly bitmask per ofactor
         std::vector<char> built;                 // per divisor slot
@@ -1074,7 +1075,9 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
                 if (e->iso_gend[di] - e->iso_gbeg[di] > e->iso_gend[main_iso] - e->iso_gbeg[main_iso])
                     main_iso = di;
             if (!(me && std::strcmp(me, "0") == 0))
-                for (int i = 0; i < niso && (int)minor_isos.size() < kMaxMerge - 1; i++) {
+                for (int i = 0; i < niso && (int)minor_isos.size() < std::min(kMaxMerge - 1, kMaxMinor) &&
+                                niso + ((int)minor_isos.size() + 1) * std::max(ndop - 1, 0) <= kMaxEntries;
+                     i++) {
                     if (std::find(dense_isos.begin(), dense_isos.end(), i) != dense_isos.end())
                         continue;
                     if (iso_row[i] == iso_row[main_iso] && e->iso_imol[i] == e->iso_imol[main_iso] &&
@@ -1317,23 +1320,33 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         // merged minor isotopes: the gather kernels need the main isotope's Doppler segments
         // of every strengths pass of this chunk
         const int *p_main_bounds = nullptr;
+        MergeView merge;
         if (!minor_isos.empty()) {
+            const size_t nminor = minor_isos.size();
             rc = e->d_bounds_main.alloc((size_t)ntc * (ndop + 1));
+            if (!rc) rc = e->d_bounds_minor.alloc((size_t)ntc * nminor * (ndop + 1));
             if (rc) return rc;
-            std::vector<double> pass_adop(ntc, 0.0);
-            std::vector<char> have(ntc, 0);
-            for (size_t a = 0; a < cu.size(); a++) {
-                pass_adop[cu[a].tpass] = ci[a * niso + main_iso].adop;
-                have[cu[a].tpass] = 1;
-            }
+            std::vector<int> pass_unit(ntc, -1);      // any unit of the pass (adop depends on T only)
+            for (size_t a = 0; a < cu.size(); a++) pass_unit[cu[a].tpass] = (int)a;
             for (int t = 0; t < ntc; t++) {
-                if (!have[t]) continue;
+                if (pass_unit[t] < 0) continue;
+                const IsoUnit *iu = ci.data() + (size_t)pass_unit[t] * niso;
                 rc = launch_segment_bounds(st, V, e->iso_gbeg[main_iso], e->iso_gend[main_iso],
-                                           pass_adop[t], e->d_bounds_main.p + (size_t)t * (ndop + 1));
+                                           iu[main_iso].adop,
+                                           e->d_bounds_main.p + (size_t)t * (ndop + 1));
+                for (size_t j = 0; j < nminor && !rc; j++) {
+                    const int mi = minor_isos[j];
+                    rc = launch_segment_bounds(st, V, e->iso_gbeg[mi], e->iso_gend[mi], iu[mi].adop,
+                                               e->d_bounds_minor.p + ((size_t)t * nminor + j) * (ndop + 1));
+                }
                 if (rc) return rc;
-                e->launches++;
+                e->launches += 1 + (int64_t)nminor;
             }
             p_main_bounds = e->d_bounds_main.p;
+            merge.nminor = (int)nminor;
+            for (size_t j = 0; j < nminor; j++) merge.iso[j] = minor_isos[j];
+            merge.main_bounds = e->d_bounds_main.p;
+            merge.minor_bounds = e->d_bounds_minor.p;
         }
         // one launch per run of equal mode; grid.y is limited to 65535 units per launch
         for (size_t u0 = 0; u0 < cu.size();) {
@@ -1359,7 +1372,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
             rc = launch_accumulate(st, V, nu, p_units + u0, p_iso_units + u0 * niso,
                                    p_iso_row, e->d_ksum.p,
                                    e->d_kmax.p, nrows, ethresh, cutoff, cmode[u0] & 15, d_out,
-                                   ksplit, e->d_partial.p, chunked, p_main_bounds);
+                                   ksplit, e->d_partial.p, chunked, merge);
             if (rc) return rc;
             e->launches += ksplit > 1 ? 2 : 1;
             if (counters) {

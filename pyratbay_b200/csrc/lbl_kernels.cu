@@ -540,11 +540,12 @@ __device__ __forceinline__ void run_multi_store(const double2 *slots, int nslots
         if (32 * q + lane < span) acc_rel[32 * q + lane] += acc[q];
 }
 
-// Candidate groups of isotope `iso` for the outputs [xmin, xmax] of one unit (same window as
-// the output-owned kernel: coarse index, tightened with the running profile maximum).
-__device__ __forceinline__ bool candidate_range(const StaticView &V, const UnitParams &U,
+// Fine cells whose groups of one isotope can reach the outputs [xmin, xmax] of a unit (the unit-
+// wide reach, tightened with the running profile maximum along the Doppler axis).
+__device__ __forceinline__ bool tile_fine_range(const StaticView &V, const UnitParams &U,
                                                 const IsoUnit &I, const double *s_doppler,
-                                                int iso, int xmin, int xmax, int *glo, int *ghi) {
+                                                int xmin, int xmax, long long *flo_out,
+                                                long long *fhi_out) {
     long long fhi = (long long)xmax * V.tstride + I.reach;
     int reach = I.reach;
     if (V.ndop >= 2) {
@@ -555,16 +556,19 @@ __device__ __forceinline__ bool candidate_range(const StaticView &V, const UnitP
     long long flo = (long long)xmin * V.tstride - reach;
     fhi = (long long)xmax * V.tstride + reach;
     if (fhi < 0 || flo > V.onwn - 1) return false;
-    if (flo < 0) flo = 0;
-    if (fhi > V.onwn - 1) fhi = V.onwn - 1;
-    if (!I.merged) {
-        if (flo >= I.dense_from) return false;   // those cells belong to the dense kernel
-        if (fhi >= I.dense_from) fhi = I.dense_from - 1;
-    }
+    *flo_out = flo < 0 ? 0 : flo;
+    *fhi_out = fhi > V.onwn - 1 ? V.onwn - 1 : fhi;
+    return true;
+}
+
+// Groups of isotope `iso` with a fine cell in [clo, chi] (inclusive), at the granularity of the
+// coarse index (the caller tests the exact cell).
+__device__ __forceinline__ int2 groups_of_cells(const StaticView &V, int iso, long long clo,
+                                                long long chi) {
+    if (chi < clo) return make_int2(0, 0);
     const int *gb = V.gbin + (size_t)iso * (V.nbins + 1);
-    *glo = gb[V.fd_binw.div((int)flo)];
-    *ghi = gb[V.fd_binw.div((int)fhi) + 1];
-    return *ghi > *glo;
+    const int glo = gb[V.fd_binw.div((int)clo)], ghi = gb[V.fd_binw.div((int)chi) + 1];
+    return ghi > glo ? make_int2(glo, ghi) : make_int2(0, 0);
 }
 
 // Two instantiations: <4 CTAs/SM, gather batch 8> for footprints of one or two passes
@@ -577,14 +581,19 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                          const double *__restrict__ ksum,
                          const unsigned long long *__restrict__ kmax, int nrows, double ethresh,
                          double cutoff, double *__restrict__ out, int ksplit,
-                         double *__restrict__ partial, const int *__restrict__ dense_bounds) {
+                         double *__restrict__ partial, MergeView M) {
     // dynamic shared memory: [8][kChunkTile] per-warp private copies of the tile, then the
     // Doppler thresholds [ndop]
     extern __shared__ double s_dyn[];
     double (*s_acc)[kChunkTile] = reinterpret_cast<double (*)[kChunkTile]>(s_dyn);
     double *s_doppler = s_dyn + 8 * kChunkTile;
     __shared__ double2 s_slot[8][32];
-    __shared__ int2 s_range[kMaxIso];               // candidate groups [glo, ghi) per isotope
+    // Work list of the tile: entry e < niso = isotope e, its groups below dense_from (all of them
+    // for an isotope that is not on the dense path); entries >= niso = (merged minor isotope,
+    // Doppler boundary): the cells where the minor isotope selects another Doppler sample than
+    // the main one (dense_kernels.cu) -- the only groups of a merged isotope left to gather.
+    __shared__ int2 s_range[kMaxEntries];           // candidate groups [glo, ghi)
+    __shared__ int2 s_cells[kMaxEntries];           // exact fine cells [clo, chi) of the entry
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < V.ndop; i += blockDim.x)
@@ -602,23 +611,41 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
     double *acc_tile = s_acc[warp];
     double2 *slots = s_slot[warp];
 
-    // candidate range of every isotope, one thread per isotope (niso <= kMaxIso == blockDim)
-    if (threadIdx.x < V.niso) {
-        const int iso = threadIdx.x;
-        int glo = 0, ghi = 0;
+    // work list, one thread per entry
+    const int nzone = M.nminor * max(V.ndop - 1, 0);
+    const int nent = V.niso + nzone;
+    for (int e = threadIdx.x; e < nent; e += blockDim.x) {
+        int2 rng = make_int2(0, 0), cells = make_int2(0, 0);
+        const int iso = e < V.niso ? e : M.iso[(e - V.niso) / (V.ndop - 1)];
+        const IsoUnit I = iso_units[(size_t)blockIdx.y * V.niso + iso];
+        long long flo, fhi;
         if (tile_hi > m0 && iso_row[iso] == row &&
-            !candidate_range(V, U, iso_units[(size_t)blockIdx.y * V.niso + iso], s_doppler, iso,
-                             m0, tile_hi - 1, &glo, &ghi))
-            glo = ghi = 0;
-        s_range[iso] = make_int2(glo, ghi);
+            tile_fine_range(V, U, I, s_doppler, m0, tile_hi - 1, &flo, &fhi)) {
+            if (e < V.niso) {
+                // cells at or above dense_from belong to the dense kernel (or to a zone entry)
+                const long long chi = min(fhi, (long long)I.dense_from - 1);
+                rng = groups_of_cells(V, iso, flo, chi);
+                cells = make_int2((int)flo, (int)min(chi + 1, 0x7fffffffLL));
+            } else if (I.merged) {
+                const int mi = (e - V.niso) / (V.ndop - 1), j = 1 + (e - V.niso) % (V.ndop - 1);
+                const int *bm = M.main_bounds + (size_t)U.tpass * (V.ndop + 1);
+                const int *bi = M.minor_bounds + ((size_t)U.tpass * M.nminor + mi) * (V.ndop + 1);
+                const long long zlo = max((long long)max(min(bm[j], bi[j]), I.dense_from), flo);
+                const long long zhi = min((long long)max(bm[j], bi[j]) - 1, fhi);   // inclusive
+                rng = groups_of_cells(V, iso, zlo, zhi);
+                cells = make_int2((int)zlo, (int)(zhi + 1));
+            }
+        }
+        s_range[e] = rng;
+        s_cells[e] = cells;
     }
     __syncthreads();
 
     if (tile_hi > m0) {
         // this warp's share [cb, ce) of the tile's chunk list (all isotopes, concatenated)
         long long total = 0;
-        for (int iso = 0; iso < V.niso; iso++) {
-            const int2 r = s_range[iso];
+        for (int e = 0; e < nent; e++) {
+            const int2 r = s_range[e];
             total += (r.y - r.x + 31) >> 5;
         }
         const int nworkers = 8 * ksplit, wid = split * 8 + warp;
@@ -629,12 +656,14 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
         const unsigned lt = (1u << lane) - 1u;
 
         long long cpos = 0;
-        for (int iso = 0; iso < V.niso && cpos < ce; iso++) {
-            const int glo = s_range[iso].x, ghi = s_range[iso].y;
+        for (int e = 0; e < nent && cpos < ce; e++) {
+            const int glo = s_range[e].x, ghi = s_range[e].y;
             const long long nchunk = (ghi - glo + 31) >> 5;
             const long long c0 = max(cb, cpos) - cpos, c1 = min(ce, cpos + nchunk) - cpos;
             cpos += nchunk;
             if (c1 <= c0) continue;
+            const int iso = e < V.niso ? e : M.iso[(e - V.niso) / (V.ndop - 1)];
+            const int2 cells = s_cells[e];
             const IsoUnit I = iso_units[(size_t)blockIdx.y * V.niso + iso];
             const int gbeg = glo + 32 * (int)c0, gend = min(ghi, glo + 32 * (int)c1);
 
@@ -658,18 +687,8 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                 Prep p;
                 p.k = 0.0; p.base = 0; p.lo = 0; p.hi = 0;
                 bool valid = false;
-                // cells >= dense_from: dense kernel, except the groups of a merged isotope
-                // that select another Doppler sample than the main isotope does there
-                bool mine = g < gend && (cur_iown < I.dense_from || I.merged);
-                if (mine && I.merged && cur_iown >= I.dense_from) {
-                    // the Doppler sample first (:278, cheap): most groups of a merged isotope
-                    // are in the dense plane and need no further preparation
-                    const int idop =
-                        V.ndop >= 2 ? doppler_index(V, s_doppler, dmul(I.adop, cur_w)) : 0;
-                    mine = !in_dense_plane(I, dense_bounds + (size_t)U.tpass * (V.ndop + 1),
-                                           cur_iown, idop);
-                }
-                if (mine)
+                // only the cells of this entry (the others: dense kernel or another entry)
+                if (g < gend && cur_iown >= cells.x && cur_iown < cells.y)
                     valid = prepare_group<kTransposed>(V, U, I, s_doppler, kthr, cutoff, cur_w,
                                                        cur_iown, cur_k, &p);
                 const int lo = max(p.lo, m0), hi = min(p.hi, tile_hi);
@@ -964,7 +983,7 @@ int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
                       const UnitParams *units, const IsoUnit *iso_units, const int *iso_row,
                       const double *ksum, const unsigned long long *kmax, int nrows,
                       double ethresh, double cutoff, int mode, double *out, int ksplit,
-                      double *partial, int chunked, const int *dense_bounds) {
+                      double *partial, int chunked, const MergeView &M) {
     if (nunits == 0 || V.nwave == 0) return 0;
     if (ksplit < 1 || !partial) ksplit = 1;
     const int tile_w = (mode == kTransposed && chunked) ? kChunkTile : kTileOutputs;
@@ -985,19 +1004,19 @@ int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
         (wide ? wide_k : narrow_k)<<<grid, 256, csmem, st>>>(
             V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial,
-            dense_bounds);
+            M);
     } else if (mode == kLinterp)
         accumulate_kernel<kLinterp><<<grid, 256, smem, st>>>(
             V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial,
-            dense_bounds);
+            M.main_bounds);
     else if (mode == kTransposed)
         accumulate_kernel<kTransposed><<<grid, 256, smem, st>>>(
             V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial,
-            dense_bounds);
+            M.main_bounds);
     else
         accumulate_kernel<kStrided><<<grid, 256, smem, st>>>(
             V, units, iso_units, iso_row, ksum, kmax, nrows, ethresh, cutoff, out, ksplit, partial,
-            dense_bounds);
+            M.main_bounds);
     PB_CUDA(cudaGetLastError());
     if (ksplit > 1) {
         dim3 rgrid((unsigned)((V.nwave + 255) / 256), (unsigned)nunits, (unsigned)nrows);

@@ -15,11 +15,24 @@ int launch_line_groups(cudaStream_t st, const unsigned int *g_start,
                        const unsigned short *g_iso, long long ngroups, int *l_group,
                        unsigned short *l_iso);
 
+// Minor isotopes merged into the main isotope's dense plane (dense_kernels.cu): the gather
+// kernels evaluate only their groups on cells where the two select different Doppler samples.
+// Doppler segments per strengths pass: main_bounds[tpass][ndop+1],
+// minor_bounds[tpass][nminor][ndop+1].
+constexpr int kMaxMinor = 7;
+struct MergeView {
+    int nminor = 0;
+    int iso[kMaxMinor] = {};
+    const int *main_bounds = nullptr;
+    const int *minor_bounds = nullptr;
+};
+constexpr int kMaxEntries = 512;   // work-list entries of a gather tile: niso + nminor*(ndop-1)
+
 int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
                       const UnitParams *units, const IsoUnit *iso_units, const int *iso_row,
                       const double *ksum, const unsigned long long *kmax, int nrows,
                       double ethresh, double cutoff, int mode, double *out, int ksplit,
-                      double *partial, int chunked, const int *dense_bounds = nullptr);
+                      double *partial, int chunked, const MergeView &M = MergeView());
 
 // mode values of launch_accumulate
 constexpr int kModeStrided = 0, kModeLinterp = 1, kModeTransposed = 2;
