@@ -1076,7 +1076,7 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
                     main_iso = di;
             if (!(me && std::strcmp(me, "0") == 0))
                 for (int i = 0; i < niso && (int)minor_isos.size() < std::min(kMaxMerge - 1, kMaxMinor) &&
-                                niso + ((int)minor_isos.size() + 1) * std::max(ndop - 1, 0) <= kMaxEntries;
+                                niso + ((int)minor_isos.size() + 1) * 2 * ndop <= kMaxEntries;
                      i++) {
                     if (std::find(dense_isos.begin(), dense_isos.end(), i) != dense_isos.end())
                         continue;

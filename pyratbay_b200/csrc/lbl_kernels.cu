@@ -590,8 +590,10 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
     __shared__ double2 s_slot[8][32];
     // Work list of the tile: entry e < niso = isotope e, its groups below dense_from (all of them
     // for an isotope that is not on the dense path); entries >= niso = (merged minor isotope,
-    // Doppler boundary): the cells where the minor isotope selects another Doppler sample than
-    // the main one (dense_kernels.cu) -- the only groups of a merged isotope left to gather.
+    // Doppler segment j of the MAIN isotope, side): the cells of that segment on which the minor
+    // isotope's lines still select a lower sample (side 0: below the start of its own segment j)
+    // or already a higher one (side 1) -- the only groups of a merged isotope left to gather
+    // (dense_kernels.cu); disjoint by construction.
     __shared__ int2 s_range[kMaxEntries];           // candidate groups [glo, ghi)
     __shared__ int2 s_cells[kMaxEntries];           // exact fine cells [clo, chi) of the entry
 
@@ -612,11 +614,11 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
     double2 *slots = s_slot[warp];
 
     // work list, one thread per entry
-    const int nzone = M.nminor * max(V.ndop - 1, 0);
+    const int nzone = M.nminor * 2 * V.ndop;
     const int nent = V.niso + nzone;
     for (int e = threadIdx.x; e < nent; e += blockDim.x) {
         int2 rng = make_int2(0, 0), cells = make_int2(0, 0);
-        const int iso = e < V.niso ? e : M.iso[(e - V.niso) / (V.ndop - 1)];
+        const int iso = e < V.niso ? e : M.iso[(e - V.niso) / (2 * V.ndop)];
         const IsoUnit I = iso_units[(size_t)blockIdx.y * V.niso + iso];
         long long flo, fhi;
         if (tile_hi > m0 && iso_row[iso] == row &&
@@ -627,11 +629,14 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
                 rng = groups_of_cells(V, iso, flo, chi);
                 cells = make_int2((int)flo, (int)min(chi + 1, 0x7fffffffLL));
             } else if (I.merged) {
-                const int mi = (e - V.niso) / (V.ndop - 1), j = 1 + (e - V.niso) % (V.ndop - 1);
+                const int mi = (e - V.niso) / (2 * V.ndop), rem = (e - V.niso) % (2 * V.ndop);
+                const int j = rem >> 1, side = rem & 1;
                 const int *bm = M.main_bounds + (size_t)U.tpass * (V.ndop + 1);
                 const int *bi = M.minor_bounds + ((size_t)U.tpass * M.nminor + mi) * (V.ndop + 1);
-                const long long zlo = max((long long)max(min(bm[j], bi[j]), I.dense_from), flo);
-                const long long zhi = min((long long)max(bm[j], bi[j]) - 1, fhi);   // inclusive
+                const int a = side ? max(bm[j], bi[j + 1]) : bm[j];
+                const int b = side ? bm[j + 1] : min(bm[j + 1], bi[j]);               // exclusive
+                const long long zlo = max((long long)max(a, I.dense_from), flo);
+                const long long zhi = min((long long)b - 1, fhi);                     // inclusive
                 rng = groups_of_cells(V, iso, zlo, zhi);
                 cells = make_int2((int)zlo, (int)(zhi + 1));
             }
@@ -662,7 +667,7 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
             const long long c0 = max(cb, cpos) - cpos, c1 = min(ce, cpos + nchunk) - cpos;
             cpos += nchunk;
             if (c1 <= c0) continue;
-            const int iso = e < V.niso ? e : M.iso[(e - V.niso) / (V.ndop - 1)];
+            const int iso = e < V.niso ? e : M.iso[(e - V.niso) / (2 * V.ndop)];
             const int2 cells = s_cells[e];
             const IsoUnit I = iso_units[(size_t)blockIdx.y * V.niso + iso];
             const int gbeg = glo + 32 * (int)c0, gend = min(ghi, glo + 32 * (int)c1);

@@ -26,7 +26,7 @@ struct MergeView {
     const int *main_bounds = nullptr;
     const int *minor_bounds = nullptr;
 };
-constexpr int kMaxEntries = 512;   // work-list entries of a gather tile: niso + nminor*(ndop-1)
+constexpr int kMaxEntries = 512;   // work-list entries of a gather tile: niso + 2*nminor*ndop
 
 int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
                       const UnitParams *units, const IsoUnit *iso_units, const int *iso_row,
