@@ -76,7 +76,9 @@ def request(op, *args):
         conn.send((op,) + args)
         status, payload = conn.recv()
     if status == "error":
+        _by_key.clear()
         raise RuntimeError(f"pb200 shim server: {payload}")
+    _by_key.clear()                 # the uploads (if any) are done: drop the references
     if status == "bytes":           # (dtype, shape) followed by the raw buffer
         dtype, shape = payload
         out = np.empty(shape, dtype)
@@ -86,13 +88,17 @@ def request(op, *args):
 
 
 _by_key = {}
+CACHE_MIN_BYTES = 1 << 20
 
 
 def static_key(arr):
-    """Content key of a static argument, cached per array object."""
+    """Content key of a static argument.  Arrays below 1 MB are hashed on every call (an
+    in-place change is honoured, as with the reference's C call); for larger ones the key is
+    cached per array object (address, shape, dtype): line lists and Voigt tables are read-only
+    in the reference."""
     arr = np.ascontiguousarray(arr)
     ident = (id(arr), arr.ctypes.data, arr.shape, str(arr.dtype))
-    key = _keys.get(ident)
+    key = _keys.get(ident) if arr.nbytes >= CACHE_MIN_BYTES else None
     if key is None:
         raw = memoryview(arr).cast("B")
         if arr.nbytes <= FULL_HASH_BYTES:
@@ -104,6 +110,7 @@ def static_key(arr):
             blocks = flat[:flat.size // 64 * 64].reshape(-1, 64)[::4096]
             digest = zlib.crc32(np.ascontiguousarray(blocks), digest)
         key = f"{arr.dtype}{arr.shape}:{arr.nbytes}:{digest:08x}"
-        _keys[ident] = key
-    _by_key[key] = arr
+        if arr.nbytes >= CACHE_MIN_BYTES:
+            _keys[ident] = key
+    _by_key[key] = arr          # kept until the request that names it has been served
     return key

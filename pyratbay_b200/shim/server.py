@@ -37,12 +37,19 @@ class Server:
             eng.set_lines(a["lwn"], a["elow"], a["gf"], a["lid"])
             eng.set_voigt(a["lorentz"], a["doppler"], a["psize"], a["pindex"], a["profile"], cutoff)
             self.engines[sig] = eng
+            # the engine holds device copies: drop the large host copies (a later engine that
+            # needs one asks the client again)
+            for key in static.values():
+                if self.arrays[key].nbytes > (16 << 20):
+                    del self.arrays[key]
         return eng
 
     def extinction(self, static, unit):
-        missing = [key for key in static.values() if key not in self.arrays]
-        if missing:
-            return "need", missing
+        sig = tuple(sorted(static.items())) + (("cutoff", unit["cutoff"]),)
+        if sig not in self.engines:
+            missing = [key for key in static.values() if key not in self.arrays]
+            if missing:
+                return "need", missing
         eng = self.engine_for(static, unit["cutoff"])
         out = eng.extinction_batch(
             [unit["temp"]], unit["moldensity"][None, :], unit["isoz"][None, :], unit["isoiext"],
