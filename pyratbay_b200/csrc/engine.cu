@@ -210,6 +210,7 @@ struct pb200_engine {
 
     // per-batch scratch (grown on demand)
     DevBuf<double> d_ksum, d_out, d_partial;
+    DevBuf<double> d_dyn;   // dynamic-grid spectra of constant-R units (kModeDynGrid)
     int sm_count = 0;
     DevBuf<unsigned long long> d_kmax, d_counters;
     // per-batch scalars (iso_row, 1/T, 1/Z, UnitParams, IsoUnit) travel in ONE copy from a
@@ -961,6 +962,27 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
     // unit's dynamic stride ofactor*scale equals the table's stride (always true when
     // wnstep/ownstep is the integer wnosamp); anything else uses the generic strided gather.
     std::vector<int> unit_mode(n_units, resolution ? kModeLinterp : kModeStrided);
+    // Constant-R / constant-wavelength grids: a unit whose dynamic grid (step ofactor*ownstep) is
+    // not much finer than the output grid is evaluated ON the dynamic grid with the chunk kernel
+    // (a constant-step problem with stride ofactor: coalesced gathers from the output-stride
+    // table built for that stride) and then interpolated (utils.h:139-163), which is what the
+    // reference does; the others gather their two samples per output point directly
+    // (kModeLinterp).  A line covers 2*cutoff/dwnstep dynamic samples but up to thousands of
+    // output points at high pressure and low wavenumber.  PB200_DYN_FACTOR: use the dynamic
+    // grid when dwnstep >= factor * mean output spacing (default 0.1; 0 = never).
+    if (resolution) {
+        double factor = 0.1;
+        if (const char *env = std::getenv("PB200_DYN_FACTOR")) factor = std::atof(env);
+        const double mean_step = (e->wn[nwave - 1] - e->wn[0]) / (double)std::max<int64_t>(nwave - 1, 1);
+        for (int u = 0; u < n_units; u++) {
+            const bool small_table =
+                (long long)e->profile_len + (long long)nlor * ndop * units[u].ofactor +
+                units[u].dnwn + 512 < 0x7fffffffLL;
+            if (factor > 0.0 && small_table && units[u].dwnstep >= factor * mean_step &&
+                units[u].dnwn >= 2 * kChunkTile)
+                unit_mode[u] = kModeDynGrid;
+        }
+    }
     // PB200_ACC_MODE=strided forces the generic gather (used by the tests to cover it).
     const char *force = std::getenv("PB200_ACC_MODE");
     const bool allow_transposed = !(force && std::strcmp(force, "strided") == 0);
@@ -1286,12 +1308,23 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
         {
             std::vector<int> members;
             while (pos < order.size() && unit_tp[order[pos]] < tp0 + ntc) members.push_back(order[pos++]);
-            auto key = [&](int u) { return unit_mode[u] | (unit_dense[u] ? 16 : 0); };
+            // units of a launch share mode, dense flag and (dynamic-grid units) the ofactor
+            auto key = [&](int u) {
+                return unit_mode[u] | (unit_dense[u] ? 16 : 0) |
+                       (unit_mode[u] == kModeDynGrid ? units[u].ofactor << 8 : 0);
+            };
             std::stable_sort(members.begin(), members.end(),
                              [&](int a, int b) { return key(a) < key(b); });
             for (int u : members) {
                 UnitParams U = units[u];
                 U.tpass = unit_tp[u] - tp0;
+                if (unit_mode[u] == kModeDynGrid) {
+                    // the unit as a constant-step problem on its own dynamic grid
+                    U.scale = 1;
+                    U.fd_scale.set(1);
+                    U.mcount = U.dnwn;
+                    U.aslot = U.out_index;      // real output row, for linterp_rows_kernel
+                }
                 cu.push_back(U);
                 cmode.push_back(key(u));
                 ci.insert(ci.end(), iso_units.begin() + (size_t)u * niso,
@@ -1367,6 +1400,45 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
                     u1 = half;
                     split_after = half;
                 }
+            }
+            if ((cmode[u0] & 15) == kModeDynGrid) {
+                // dynamic-grid units of one ofactor: output-stride table for that stride, chunk
+                // kernel on the dynamic grid into scratch rows, 2-point interpolation to the output
+                const int of = cu[u0].ofactor, dn = cu[u0].dnwn;
+                rc = ensure_transposed(e, of);
+                if (rc) return rc;
+                StaticView V2 = e->view();
+                V2.nwave = dn;
+                if (counters) {   // first: the scratch launches renumber out_index on the device
+                    rc = launch_counters(st, V, (int)(u1 - u0), p_units + u0, p_iso_units + u0 * niso,
+                                         p_iso_row, e->d_ksum.p, e->d_kmax.p, nrows, ethresh,
+                                         cutoff, 1, e->d_counters.p);
+                    if (rc) return rc;
+                    if (V.ngroups > 0) e->launches++;
+                }
+                const size_t row_doubles = (size_t)nrows * (size_t)dn;
+                const size_t per_launch = std::max<size_t>(1, ((size_t)1 << 28) / row_doubles);  // 2 GiB
+                for (size_t a0 = u0; a0 < u1; a0 += per_launch) {
+                    const size_t a1 = std::min(u1, a0 + per_launch);
+                    const int nd = (int)(a1 - a0);
+                    rc = e->d_dyn.alloc((size_t)nd * row_doubles);
+                    if (rc) return rc;
+                    // rows of the scratch are numbered within the launch
+                    for (size_t a = a0; a < a1; a++) cu[a].out_index = (int)(a - a0);
+                    PB_CUDA(cudaMemcpyAsync(e->d_stage.p + off_units + sizeof(UnitParams) * a0,
+                                            cu.data() + a0, sizeof(UnitParams) * nd,
+                                            cudaMemcpyHostToDevice, st));
+                    rc = launch_accumulate(st, V2, nd, p_units + a0, p_iso_units + a0 * niso,
+                                           p_iso_row, e->d_ksum.p, e->d_kmax.p, nrows, ethresh,
+                                           cutoff, kModeTransposed, e->d_dyn.p, 1, nullptr, 1);
+                    if (!rc)
+                        rc = launch_linterp_rows(st, V, nd, p_units + a0, e->d_dyn.p, dn, nrows,
+                                                 d_out);
+                    if (rc) return rc;
+                    e->launches += 2;
+                }
+                u0 = u1;
+                continue;
             }
             const int nu = (int)(u1 - u0);
             rc = launch_accumulate(st, V, nu, p_units + u0, p_iso_units + u0 * niso,

@@ -787,6 +787,28 @@ accumulate_chunks_kernel(StaticView V, const UnitParams *__restrict__ units,
     }
 }
 
+// Output stage of a constant-R / constant-wavelength grid from a unit's DYNAMIC-grid spectrum
+// (utils.h:139-163 linterp, _extcoeff.c:320-332): ext[i] = 2-point interpolation of ktmp at
+// wn[i].  ktmp rows [nunits, nrows, dn] come from the chunk kernel run on the dynamic grid
+// (engine.cu: units whose dynamic grid is not much finer than the output grid); the unit's
+// real output index travels in UnitParams::aslot.
+__global__ void __launch_bounds__(256)
+linterp_rows_kernel(StaticView V, const UnitParams *__restrict__ units,
+                    const double *__restrict__ ktmp, int dn, int nrows, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V.nwave) return;
+    const UnitParams U = units[blockIdx.y];
+    const int row = blockIdx.z;
+    const double wn_i = V.wn[i];
+    const int x0 = (int)ddiv(dsub(wn_i, V.wn0), U.dwnstep);
+    const double *src = ktmp + ((size_t)U.out_index * nrows + row) * (size_t)dn;
+    const double k0 = (x0 >= 0 && x0 < dn) ? src[x0] : 0.0;
+    const double k1 = (x0 + 1 >= 0 && x0 + 1 < dn) ? src[x0 + 1] : 0.0;
+    const double wlo = dadd(V.wn0, dmul(U.dwnstep, (double)x0));
+    out[((size_t)U.aslot * nrows + row) * (size_t)V.nwave + i] =
+        (k0 * (wlo + U.dwnstep - wn_i) + k1 * (wn_i - wlo)) / U.dwnstep;
+}
+
 // Sum the ksplit partial spectra of every (unit, row) in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const UnitParams *__restrict__ units, const double *__restrict__ partial,
@@ -1028,6 +1050,15 @@ int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
         reduce_partials_kernel<<<rgrid, 256, 0, st>>>(units, partial, nrows, ksplit, V.nwave, out);
         PB_CUDA(cudaGetLastError());
     }
+    return 0;
+}
+
+int launch_linterp_rows(cudaStream_t st, const StaticView &V, int nunits, const UnitParams *units,
+                        const double *ktmp, int dn, int nrows, double *out) {
+    if (nunits == 0 || V.nwave == 0) return 0;
+    dim3 grid((unsigned)((V.nwave + 255) / 256), (unsigned)nunits, (unsigned)nrows);
+    linterp_rows_kernel<<<grid, 256, 0, st>>>(V, units, ktmp, dn, nrows, out);
+    PB_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -34,8 +34,15 @@ int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
                       double ethresh, double cutoff, int mode, double *out, int ksplit,
                       double *partial, int chunked, const MergeView &M = MergeView());
 
+// Interpolate dynamic-grid spectra ktmp[nunits, nrows, dn] onto the output grid (units[].aslot =
+// output index of the unit, units[].out_index = its row in ktmp).
+int launch_linterp_rows(cudaStream_t st, const StaticView &V, int nunits, const UnitParams *units,
+                        const double *ktmp, int dn, int nrows, double *out);
+
 // mode values of launch_accumulate
 constexpr int kModeStrided = 0, kModeLinterp = 1, kModeTransposed = 2;
+// host only: constant-R unit evaluated on its dynamic grid (chunk kernel) + linterp_rows_kernel
+constexpr int kModeDynGrid = 3;
 
 // Build the output-stride copy of the Voigt table (one-time; synchronises `st`).
 int launch_transpose(cudaStream_t st, int nprof, const long long *src, const long long *dst,

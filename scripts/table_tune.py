@@ -23,8 +23,13 @@ def main():
     settings = sys.argv[1:] or ["occ=0.25,span=24"]
     nlines = int(float(os.environ.get("NLINES", "1e8")))
     w = workloads.table_workload(nlines)
-    spec = Spectrum(wnlow=w.inputs["wnlow"], wnhigh=w.inputs["wnhigh"], wnstep=w.wnstep,
-                    wnosamp=w.wnosamp)
+    resolution = float(os.environ.get("RESOLUTION", "0"))   # constant-R variant of the table
+    if resolution:
+        spec = Spectrum(wnlow=w.inputs["wnlow"], wnhigh=w.inputs["wnhigh"], wnstep=1.0,
+                        resolution=resolution)
+    else:
+        spec = Spectrum(wnlow=w.inputs["wnlow"], wnhigh=w.inputs["wnhigh"], wnstep=w.wnstep,
+                        wnosamp=w.wnosamp)
     lwn, elow, gf, iso, _ = w.make_lines()
     eng = Engine(0)
     eng.set_grid(spec.wn, spec.own, spec.odivisors)
@@ -45,9 +50,10 @@ def main():
         os.environ["PB200_DENSE"] = kv.get("dense", "1")
         os.environ["PB200_DENSE_MIN_OCC"] = kv.get("occ", "0.25")
         os.environ["PB200_DENSE_MIN_SPAN"] = kv.get("span", "24")
+        os.environ["PB200_DYN_FACTOR"] = kv.get("dyn", "0.1")
         for _ in range(2):
-            eng.extinction_batch(temps, dens, isoz, w.iso_mol_index, 1, 1e-30, 0, 0,
-                                 out_device_ptr=out.data_ptr())
+            eng.extinction_batch(temps, dens, isoz, w.iso_mol_index, 1, 1e-30, 0,
+                                 1 if resolution else 0, out_device_ptr=out.data_ptr())
         t = eng.last_timing()
         rec = {"setting": setting, "accumulate_ms": round(float(t["accumulate_ms"]), 1),
                "dense_ms": round(eng.dense_ms(), 1), "dense_unit_isos": eng.dense_units(),

@@ -268,3 +268,27 @@ def test_compute_opacity_leaves_the_table_on_the_device(tmp_path):
     direct = pyrat.engine.extinction_batch(temps, dens, isoz, w.iso_mol_index, 1, 1e-30, 0, 0)
     assert np.array_equal(direct[:, 0].reshape(4, 7, 2000), ex.etable)
     assert ex.etable.max() > 0
+
+
+@pytest.mark.parametrize("factor", ["0", "0.1", "0.001"])
+def test_constant_resolution_dynamic_grid_path(factor, monkeypatch):
+    """Constant-R grid: units evaluated on their dynamic grid with the chunk kernel and then
+    interpolated (PB200_DYN_FACTOR: never / default split / every unit that qualifies) against the
+    oracle, with equal counters; add = 0 and 1."""
+    monkeypatch.setenv("PB200_DYN_FACTOR", factor)
+    case = helpers.synthetic_case(nlines=60000, wnlow=9000.0, wnhigh=9400.0, resolution=9000.0,
+                                  nlayers=11)
+    temps, dens = case.atm.temp, case.atm.d
+    isoz = helpers.partition(case, temps).T
+    orc = helpers.oracle_module()
+    for add in (0, 1):
+        eng = _engine(case)
+        got, cnt = eng.extinction_batch(temps, dens, isoz, case.iso_mol_index, 1, case.ethresh,
+                                        add, 1, counters=True)
+        eng.close()
+        for u in range(len(temps)):
+            ext = np.zeros((1, case.spec.nwave))
+            c = np.zeros(4, np.int64)
+            orc.extinction(ext, *case.unit_args(temps[u], dens[u], isoz[u]), 0, add, 1, counters=c)
+            assert np.array_equal(cnt[u, :4], c)
+            assert np.max(np.abs(got[u, 0] - ext[0])) / ext[0].max() < TOL_PEAK
