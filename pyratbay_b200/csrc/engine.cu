@@ -1013,7 +1013,8 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
     }
 
     // Dense-convolution path (dense_kernels.cu) for isotopes whose groups fill a large share of
-    // the fine grid: the gather kernels skip those isotopes and the dense kernel adds them.
+    // the fine grid: the gather kernels leave out the cells the dense kernel owns (per unit and
+    // isotope everything at or above `dense_from`), the dense kernel adds them afterwards.
     // Only where its premise holds: constant-step grid on the output-stride table, windows that
     // are translation invariant (cutoff/dwnstep not within 1e-6 of an integer, so that the
     // reference's (int)(idwn +- cutoff/dwnstep) is idwn +- a constant), footprints that fit
