@@ -129,7 +129,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    warmup = min(args.warmup, 1)
+    warmup = min(args.warmup, 5)     # every step is 2-4 s of wall time on the host cores
     base, err = run_cpu_baseline(args, args.steps, warmup)
     if base is None:
         print(json.dumps({"impl": "reference", "unavailable": "cpu_baseline.py failed: " + err}))
