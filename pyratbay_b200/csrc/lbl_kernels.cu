@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <cstdint>
 #include <vector>
 
@@ -1022,8 +1023,10 @@ int launch_accumulate(cudaStream_t st, const StaticView &V, int nunits,
         // more than 48 KB of dynamic shared memory needs the per-device opt-in (not the case
         // for 512-output tiles unless the Doppler grid is huge)
         // outputs a line can cover: 2*cutoff/wnstep (+1); three or more passes of 32 -> wide variant
-        const bool wide = V.tstride > 0 && V.cut_fine != 0x7fffffff &&
-                          2LL * V.cut_fine / V.tstride >= 96;
+        bool wide = V.tstride > 0 && V.cut_fine != 0x7fffffff &&
+                    2LL * V.cut_fine / V.tstride >= 96;
+        if (const char *force = std::getenv("PB200_CHUNK_FORM"))   // "narrow" / "wide" (tuning)
+            wide = force[0] == 'w';
         auto narrow_k = accumulate_chunks_kernel<PB200_CHUNK_MINBLOCKS, PB200_CHUNK_UNROLL>;
         auto wide_k = accumulate_chunks_kernel<3, 16>;
         if (csmem > 48 * 1024)

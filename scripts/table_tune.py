@@ -51,6 +51,10 @@ def main():
         os.environ["PB200_DENSE_MIN_OCC"] = kv.get("occ", "0.25")
         os.environ["PB200_DENSE_MIN_SPAN"] = kv.get("span", "24")
         os.environ["PB200_DYN_FACTOR"] = kv.get("dyn", "0.1")
+        if "form" in kv:
+            os.environ["PB200_CHUNK_FORM"] = kv["form"]
+        else:
+            os.environ.pop("PB200_CHUNK_FORM", None)
         for _ in range(2):
             eng.extinction_batch(temps, dens, isoz, w.iso_mol_index, 1, 1e-30, 0,
                                  1 if resolution else 0, out_device_ptr=out.data_ptr())
