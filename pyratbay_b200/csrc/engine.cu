@@ -1041,11 +1041,12 @@ static int run_batch(pb200_engine *e, int n_units, const double *unit_temp,
                     dense_isos.push_back(i);
         }
         if (!dense_isos.empty()) {
-            // A footprint narrower than ~24 outputs leaves the dense kernel's register tile
-            // mostly idle (a warp walks 16 + span - 1 cells whatever the span), and footprints
+            // A footprint narrower than ~16 outputs leaves the dense kernel's register tile
+            // mostly idle (a half-warp walks 15 + span cells whatever the span), and footprints
             // grow with wavenumber (Doppler width): per unit and isotope the cells below
-            // `dense_from` (narrow Doppler samples) stay with the gather kernels.
-            int min_span = 24;
+            // `dense_from` (narrow Doppler samples) stay with the gather kernels.  Measured on
+            // the bench table: 8 / 16 / 24 / 32 outputs -> flat within 1.5 % around 16.
+            int min_span = 16;
             if (const char *ms = std::getenv("PB200_DENSE_MIN_SPAN")) min_span = std::atoi(ms);
             const int cut_fine = cutoff > 0.0 ? (int)std::min(cutoff / ownstep + 1.0, 2.0e9)
                                               : 0x7fffffff;
