@@ -402,3 +402,33 @@ def test_nearest_thresholds_reproduce_the_nearest_sample_search():
         assert np.array_equal(got, want)
     with pytest.raises(PB200Error):
         nearest_thresholds(np.array([1.0, 1.0, 2.0]))
+
+
+def test_shim_static_keys_and_install(tmp_path):
+    """Drop-in shim (pyratbay_b200/shim), host side only: content keys of static arguments
+    (small arrays re-hashed on every call so an in-place change is seen, large ones cached per
+    array object) and the two forwarding modules written into a reference lib/ directory."""
+    from pyratbay_b200.shim import client, install_into
+    small = np.arange(1000, dtype=np.float64)
+    k1 = client.static_key(small)
+    small[10] += 1.0
+    assert client.static_key(small) != k1
+    assert client.static_key(small.copy()) == client.static_key(small)     # content, not identity
+    big = np.zeros(200_000, np.float64)                                     # 1.6 MB: cached
+    kb = client.static_key(big)
+    assert client.static_key(big) == kb and kb != client.static_key(np.ones(200_000))
+    assert client.static_key(np.zeros(200_000, np.float64)) == kb
+    assert client.static_key(np.arange(5, dtype=np.int64)) != client.static_key(np.arange(5.0))
+    lib = tmp_path / "lib"
+    lib.mkdir()
+    (lib / "_extcoeff.cpython-312-x86_64-linux-gnu.so").write_bytes(b"x")
+    (lib / "_trapezoid.cpython-312-x86_64-linux-gnu.so").write_bytes(b"x")
+    install_into(str(lib))
+    names = sorted(os.listdir(lib))
+    assert names == ["_extcoeff.py", "_trapezoid.cpython-312-x86_64-linux-gnu.so", "vprofile.py"]
+    assert "pyratbay_b200.shim._extcoeff" in (lib / "_extcoeff.py").read_text()
+    import inspect
+    from pyratbay_b200.shim import _extcoeff, vprofile
+    assert len(inspect.signature(_extcoeff.extinction).parameters) == 27    # _extcoeff.c:114-123
+    assert list(inspect.signature(vprofile.grid).parameters) == [
+        "profile", "psize", "index", "lorentz", "doppler", "dwn", "verb"]  # vprofile.c:53-57
