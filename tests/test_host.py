@@ -432,3 +432,32 @@ def test_shim_static_keys_and_install(tmp_path):
     assert len(inspect.signature(_extcoeff.extinction).parameters) == 27    # _extcoeff.c:114-123
     assert list(inspect.signature(vprofile.grid).parameters) == [
         "profile", "psize", "index", "lorentz", "doppler", "dwn", "verb"]  # vprofile.c:53-57
+
+
+def test_streaming_opacity_writer_matches_write_opacity(tmp_path):
+    """io.OpacityWriter (rows appended while later ones are still being computed) writes the
+    members np.savez writes in io.write_opacity (io/io.py:570-606): same arrays, dtypes, units."""
+    from pyratbay_b200 import io
+    rng = np.random.default_rng(4)
+    temp, press, wn = np.linspace(300, 3000, 4), np.logspace(-6, 2, 5), np.linspace(1000, 1100, 7)
+    table = rng.random((4, 5, 7))
+    a, b = str(tmp_path / "a.npz"), str(tmp_path / "b")      # .npz appended like np.savez does
+    io.write_opacity(a, "H2O", temp, press, wn, table)
+    with io.OpacityWriter(b, "H2O", temp, press, wn) as w:
+        flat = table.reshape(20, 7)
+        w.write(flat[:3])
+        w.write(flat[3:11])
+        w.write(flat[11:])
+    fa, fb = np.load(a, allow_pickle=True), np.load(b + ".npz", allow_pickle=True)
+    assert sorted(fa.files) == sorted(fb.files)
+    for key in fa.files:
+        assert fa[key].dtype == fb[key].dtype and fa[key].shape == fb[key].shape
+        if key == "units":
+            assert fa[key].item() == fb[key].item()
+        else:
+            assert np.array_equal(fa[key], fb[key])
+    assert all(np.array_equal(x, y) if isinstance(x, np.ndarray) else x == y
+               for x, y in zip(io.read_opacity(a), io.read_opacity(b + ".npz")))
+    with pytest.raises(ValueError):                          # incomplete table
+        with io.OpacityWriter(str(tmp_path / "c.npz"), "H2O", temp, press, wn) as w:
+            w.write(flat[:5])
