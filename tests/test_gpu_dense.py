@@ -218,3 +218,29 @@ def test_two_dense_planes_and_merged_minors(monkeypatch):
     assert np.array_equal(cnt[:, :4], wcnt)
     assert _peak_err(got, want) < TOL_PEAK
     assert used > 2 * len(temps)        # two planes plus merged isotopes
+
+
+def test_dense_path_with_chunked_strength_passes(monkeypatch):
+    """Strength passes forced into chunks of 2 temperatures and gather launches of at most 3
+    units: the dense path's per-pass state (Doppler segments of main and minor isotopes, dense
+    planes) is chunk-relative; same bits as the unchunked batch."""
+    case = helpers.synthetic_case(nlines=150_000, wnlow=9000.0, wnhigh=9400.0, wnstep=0.25,
+                                  wnosamp=360, cutoff=10.07, extent=60.0, nlayers=7, ndop=40)
+    temps, dens = case.atm.temp, case.atm.d
+    isoz = helpers.partition(case, temps).T
+    occ = np.bincount(case.isoid, minlength=4) / len(case.spec.own)
+    monkeypatch.setenv("PB200_DENSE_MIN_OCC", f"{0.5 * (occ[0] + occ[1]) * 0.8:.5f}")
+    args = (temps, dens, isoz, case.iso_mol_index, 1, case.ethresh, 0, 0)
+    eng = _engine(case)
+    base = eng.extinction_batch(*args)
+    assert eng.dense_units() > len(temps)
+    eng.close()
+    monkeypatch.setenv("PB200_TP_CHUNK", "2")
+    monkeypatch.setenv("PB200_MAX_UNITS_PER_LAUNCH", "3")
+    eng = _engine(case)
+    chunked = eng.extinction_batch(*args)
+    assert eng.dense_units() > len(temps)
+    eng.close()
+    assert np.array_equal(chunked, base)
+    want, _ = _oracle(case, temps, dens, isoz, 0)
+    assert _peak_err(base, want) < TOL_PEAK
