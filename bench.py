@@ -585,7 +585,7 @@ def run_table(args):
     roofline["note"] = (
         "algorithmic HBM bytes of the whole accumulate stage over its device time.  The stage is "
         "compute/delivery bound, not HBM bound (the algorithm needs 1.3 TB per table): the dense "
-        "kernel runs on the fp64 FMA pipe (65 % active, profiles/r02c_dense_merged.txt), the gather "
+        "kernel runs on the fp64 FMA pipe (62-66 % active, profiles/r02f_dense_final.txt), the gather "
         "kernel on L2->SM bandwidth; roofline_fp64 is the meaningful ceiling (DESIGN.md section 5)")
 
     cpu_baseline = None
